@@ -1,0 +1,182 @@
+/* pcreg.h -- C ABI of the B200-native PCReg alignment hot path (libpcreg_b200.so).
+ *
+ * This is the drop-in boundary: a MEX gateway (pcreg_b200/csrc/pcreg_mex.cpp), the Python
+ * ctypes mirror (pcreg_b200/api.py) and any other host bind exactly these symbols.  No MATLAB,
+ * torch or C++ types cross it.  The reference (LCJebe/PCReg) is MATLAB-only and has no FFI; each
+ * entry point cites the reference .m interface it replaces (file:line into the reference tree).
+ *
+ * Conventions (reference: quickTF.m:5-7, estimateTransform.m:66-71)
+ *   - Point sets are N x 3 COLUMN-MAJOR (MATLAB memory order): x[0..N), y at +ld, z at +2*ld
+ *     elements; `is_double` selects float64 (1) or float32 (0) element type.
+ *   - Rigid transforms are 4 x 4 ROW-VECTOR form T = [R 0; t 1],  p' = [p 1] * T, stored
+ *     COLUMN-MAJOR (MATLAB order): element (r,c) at T16[c*4 + r].  Batches are contiguous 16-double
+ *     records.
+ *   - Indices are 0-based at this boundary (the MATLAB shims add 1).
+ *   - Every call returns int status: 0 = OK; > 0 = degenerate input ("the reference returns []");
+ *     < 0 = CUDA / allocation / argument error, text via pcreg_last_error().
+ *   - There is NO CPU fallback: without a usable CUDA device every compute call returns
+ *     PCREG_ERR_CUDA.
+ */
+#ifndef PCREG_H
+#define PCREG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCREG_OK              0
+#define PCREG_DEGENERATE      1     /* reference would return [] */
+#define PCREG_ERR_ARG        -1
+#define PCREG_ERR_CUDA       -2
+#define PCREG_ERR_ALLOC      -3
+#define PCREG_ERR_STATE      -4     /* not initialised / bad handle */
+
+typedef struct pcreg_model pcreg_model;   /* opaque, GPU-resident model cloud */
+
+/* ---- library lifetime ------------------------------------------------------------------- */
+/* One process drives ONE GPU (one process per GPU; multi-GPU = one rank per GPU sharding the
+ * hypothesis batch, see pcreg_b200/sharded.py).  devices[0] is the CUDA ordinal; ndev must be 1.
+ * devices == NULL selects ordinal 0. */
+int  pcreg_init(const int* devices, int ndev);
+int  pcreg_shutdown(void);
+const char* pcreg_last_error(void);
+/* Number of kernels this library launched since pcreg_init (bench.py's gpu_launches claim). */
+int64_t pcreg_launch_count(void);
+/* ABI version of this header (bumped on any signature change). */
+int  pcreg_abi_version(void);
+
+/* ---- model cloud handle ----------------------------------------------------------------- */
+typedef struct {
+    int     build_grid;        /* 1: also build the uniform grid + occupancy pyramid (device counting sort) */
+    double  cell_size;         /* grid cell edge; <= 0: automatic (about cells_per_point cells per point)   */
+    double  cells_per_point;   /* automatic sizing target, <= 0 -> 16                                       */
+    int64_t max_cells;         /* cap on level-0 cells, <= 0 -> 2^27                                        */
+    uint64_t shuffle_seed;     /* seed of the brute-force scan order permutation (any value; 0 is fine)     */
+} pcreg_model_opts;
+
+/* Upload a model cloud (the dense CT/MRI cloud every driver loads once: completeExperiment.m:15,
+ * slideMatchingWindow_v2.m:15; class single as written by upsampleMesh.m:21).  Builds the FP32
+ * float4 scan array, the FP64 array used for exact re-checks and, if asked, the grid. */
+int  pcreg_model_create(const void* xyz, int is_double, int64_t n, int64_t ld,
+                        const pcreg_model_opts* opts, pcreg_model** out);
+int  pcreg_model_destroy(pcreg_model* m);
+int64_t pcreg_model_size(const pcreg_model* m);
+/* Grid facts for roofline accounting: dims[3], cell size, number of non-empty level-0 cells. */
+int  pcreg_model_grid_info(const pcreg_model* m, int32_t dims[3], double* cell_size, int64_t* occupied);
+
+/* ---- nearest neighbour (knnsearch(model, q, 'K', 1) semantics: Euclidean, FP64, ties -> smallest
+ *      index; the reference's only literal cloud->cloud 1-NN loop is ColorCodeModel.m:15-18) ---- */
+#define PCREG_NN_BRUTE 0
+#define PCREG_NN_GRID  1
+int  pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t nq, int64_t ld,
+                     int nn_kind, int32_t* idx /*[nq]*/, double* d2 /*[nq] squared distance, may be NULL*/);
+
+/* ---- AlignPoints family (AlignPoints.m:1-29, AlignPoints_KNN.m:1-60, AlignPoints_knn.m:1-43,
+ *      AlignPoints_weighted.m:1-49, AlignPoints_c.m:1-44, AlignPoints_KNN_c.m:1-57), batched over
+ *      neighbourhoods ---------------------------------------------------------------------------- */
+#define PCREG_ALIGN_PLAIN     0   /* AlignPoints          */
+#define PCREG_ALIGN_KNN_FRAC  1   /* AlignPoints_KNN      */
+#define PCREG_ALIGN_KNN_ABS   2   /* AlignPoints_knn      */
+#define PCREG_ALIGN_WEIGHTED  3   /* AlignPoints_weighted */
+#define PCREG_ALIGN_C         4   /* AlignPoints_c        */
+#define PCREG_ALIGN_KNN_C     5   /* AlignPoints_KNN_c    */
+typedef struct {
+    double  k_frac;     /* 0.85  (AlignPoints_KNN.m:20)          */
+    int64_t k_abs;      /* AlignPoints_knn's K                   */
+    double  R_w;        /* 3.5   (AlignPoints_weighted.m:16)     */
+    double  r_local;    /* 2.0   (AlignPoints_c.m:13)            */
+    int64_t min_local;  /* 25    (AlignPoints_c.m:14)            */
+    int     C1;         /* AlignPoints_KNN varargin{1}           */
+    int     C2;         /* AlignPoints_KNN varargin{2}           */
+} pcreg_align_opts;
+void pcreg_align_opts_default(pcreg_align_opts* o);
+/* pts: ntotal x 3 column-major (ld = leading dimension), neighbourhood b = rows
+ * offsets[b] .. offsets[b+1]-1.  Outputs: pts_aligned (same shape/class/ld as pts), coeff9
+ * [nbatch][9] column-major 3x3 coeff_unambig, c3 [nbatch][3] centroid, status [nbatch]
+ * (0 ok, 1 = reference returns []; rows of that neighbourhood are then left untouched). */
+int  pcreg_align_points(int kind, const void* pts, int is_double, int64_t ld,
+                        const int64_t* offsets, int64_t nbatch, const pcreg_align_opts* opts,
+                        void* pts_aligned, double* coeff9, double* c3, int32_t* status);
+
+/* ---- estimateTransform.m:2-74, batched ------------------------------------------------------ */
+/* p1, p2: ntotal x 3 column-major doubles (ld), problem b = rows offsets[b]..offsets[b+1]-1,
+ * optional weights w[ntotal] (NULL = 1).  T16[b] satisfies [p2,1]*T = [p1,1].  status[b] = 1
+ * where the reference's rank guard (estimateTransform.m:11-14) returns [].
+ * reflection_fix = 0 reproduces the reference (R = V*U', no determinant check). */
+int  pcreg_kabsch_batch(const double* p1, const double* p2, const double* w, int64_t ld,
+                        const int64_t* offsets, int64_t nbatch, int reflection_fix,
+                        double* T16, int32_t* status);
+
+/* ---- ransac.m:21-116 hypothesis scoring, sample triplets supplied by the host ---------------- */
+typedef struct {
+    double thDist;          /* compared against SQUARED distances (ransac.m:49)   */
+    double thInlrRatio;     /* thInlr = round(thInlrRatio * P) (ransac.m:28)       */
+    int    refine;          /* coef.REFINE (ransac.m:53-61)                        */
+    int    reflection_fix;  /* 0 = reference                                       */
+} pcreg_ransac_opts;
+/* p1, p2: P x 3 column-major doubles (ld).  triplets: nhyp x 3, 0-based, hypothesis-major
+ * (triplets[3*h+k]).  Outputs: T16_best (16), inl_idx [P] (first *n_inl entries valid, 0-based,
+ * ascending), n_succ, max_inl, best_hyp (-1 on failure), optional per-hypothesis counts
+ * inl_counts[nhyp] (3-point fit) and inl_counts_refined[nhyp], optional T16_all [nhyp][16]
+ * (the TForms kept by ransac.m:60/63; NaN-filled where none).  Returns PCREG_DEGENERATE where
+ * ransac.m:75-89 returns T = []. */
+int  pcreg_ransac_score(const double* p1, const double* p2, int64_t P, int64_t ld,
+                        const int32_t* triplets, int64_t nhyp, const pcreg_ransac_opts* opts,
+                        double* T16_best, int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ,
+                        int64_t* max_inl, int64_t* best_hyp,
+                        int32_t* inl_counts, int32_t* inl_counts_refined, double* T16_all);
+
+/* ---- batched ICP (composition of quickTF.m, the 85 % trim rule AlignPoints_KNN.m:20-26, the
+ *      weights of AlignPoints_weighted.m:16-18, estimateTransform.m:41-71 and ransac.m's
+ *      score / first-arg-best structure around an exact NN step) --------- */
+#define PCREG_ICP_PLAIN    0
+#define PCREG_ICP_KNN      1
+#define PCREG_ICP_WEIGHTED 2
+typedef struct {
+    int    mode;            /* PCREG_ICP_*                                             */
+    int    iters;           /* pose updates; one extra NN pass scores the final pose   */
+    double k_frac;          /* KNN: keep round(k_frac * n_kept) smallest residuals     */
+    double R_w;             /* WEIGHTED: w = max(R_w - r, 0)                           */
+    double thDist2;         /* > 0: reject correspondences with d^2 >= thDist2         */
+    int    nn;              /* PCREG_NN_BRUTE / PCREG_NN_GRID                          */
+    int    reflection_fix;  /* 0 = reference                                           */
+} pcreg_icp_opts;
+void pcreg_icp_opts_default(pcreg_icp_opts* o);
+/* src: ns x 3 column-major; w_src[ns] optional; T0_16 [nhyp][16] initial poses.  Outputs (any
+ * may be NULL except T16): T16 [nhyp][16], rmse [nhyp], n_used [nhyp], status [nhyp] (0 ok,
+ * 1 = fewer than 3 usable correspondences at some iteration: pose frozen there), idx
+ * [nhyp][ns] final correspondences, rmse_hist [nhyp][iters+1], best = first-index arg-min of
+ * rmse (-1 if all NaN). */
+int  pcreg_icp_batch(const pcreg_model* m, const void* src, int is_double, int64_t ns, int64_t ld,
+                     const double* w_src, const double* T0_16, int64_t nhyp,
+                     const pcreg_icp_opts* opts,
+                     double* T16, double* rmse, int32_t* n_used, int32_t* status, int32_t* idx,
+                     double* rmse_hist, int64_t* best);
+
+/* Same, with every array already resident on the device the library was initialised on
+ * (src as float64 column-major, ld = ns) and launched on `stream` (a cudaStream_t passed as
+ * void*; NULL = default stream).  Asynchronous: the caller synchronises the stream.  `best` is
+ * a device int64.  This is the entry bench.py's device-resident `value` is timed through. */
+int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
+                         const double* d_w_src, const double* d_T0_16, int64_t nhyp,
+                         const pcreg_icp_opts* opts,
+                         double* d_T16, double* d_rmse, int32_t* d_n_used, int32_t* d_status,
+                         int32_t* d_idx, double* d_rmse_hist, int64_t* d_best, void* stream);
+
+/* Timing / accounting of the most recent pcreg_icp_batch{,_dev} or pcreg_nn_search call,
+ * measured with CUDA events on the launching stream (bench.py's roofline numbers):
+ *   out[0] = NN kernel launches, out[1] = total NN kernel ms, out[2] = NN queries,
+ *   out[3] = (query, model point) pairs evaluated by brute force,
+ *   out[4] = update (select + 17-sum + Kabsch) kernel launches, out[5] = their total ms,
+ *   out[6] = correspondences reduced, out[7] = grid points visited (exact count, grid NN),
+ *   out[8] = grid cells visited.
+ * Event timing is only collected when enabled (it serialises nothing but adds event records). */
+int  pcreg_set_profiling(int enabled);
+int  pcreg_last_profile(double out[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCREG_H */

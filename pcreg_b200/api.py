@@ -1,0 +1,285 @@
+"""Host-side mirror of the reference's MATLAB interface for the alignment hot path.
+
+Same names, argument meaning, return values and error behaviour as the reference .m functions
+(AlignPoints.m, AlignPoints_KNN.m, AlignPoints_knn.m, AlignPoints_weighted.m, AlignPoints_c.m,
+AlignPoints_KNN_c.m, estimateTransform.m, ransac.m) plus the batched / ICP forms; everything
+computes in libpcreg_b200.so on the GPU through the C ABI of include/pcreg.h.  "Returns []" in the
+reference is ``None`` here.  Indices are 0-based (Python), transforms are 4x4 row-vector form
+T = [R 0; t 1] with [p 1] @ T (quickTF.m:5-7).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import AlignOpts, IcpOpts, ModelOpts, PcregError, RansacOpts  # noqa: F401
+
+NN_BRUTE, NN_GRID = 0, 1
+ICP_PLAIN, ICP_KNN, ICP_WEIGHTED = 0, 1, 2
+ALIGN_PLAIN, ALIGN_KNN_FRAC, ALIGN_KNN_ABS, ALIGN_WEIGHTED, ALIGN_C, ALIGN_KNN_C = range(6)
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+def _cm_points(pts):
+    """N x 3 array -> (column-major array, is_double, n).  float32 stays float32 (class single)."""
+    pts = np.asarray(pts)
+    if pts.ndim != 2 or pts.shape[1] != 3:
+        raise ValueError("points must be N x 3")
+    if pts.dtype != np.float32:
+        pts = pts.astype(np.float64, copy=False)
+    a = np.asfortranarray(pts)
+    return a, int(a.dtype == np.float64), a.shape[0]
+
+
+def _T_to_abi(T):
+    """(..., 4, 4) math layout -> contiguous MATLAB column-major records."""
+    T = np.asarray(T, dtype=np.float64)
+    return np.ascontiguousarray(np.swapaxes(T, -1, -2))
+
+
+def _T_from_abi(buf, n=None):
+    a = np.asarray(buf, dtype=np.float64)
+    a = a.reshape(4, 4) if n is None else a.reshape(n, 4, 4)
+    return np.ascontiguousarray(np.swapaxes(a, -1, -2))
+
+
+# ------------------------------------------------------------------------------------------------
+# model handle
+# ------------------------------------------------------------------------------------------------
+class Model:
+    """GPU-resident model cloud (pcreg_model_create).  ``grid=True`` also builds the uniform grid."""
+
+    def __init__(self, pts, grid: bool = False, cell_size: float = 0.0, cells_per_point: float = 0.0,
+                 max_cells: int = 0, shuffle_seed: int = 0):
+        lib = L.lib()
+        a, is_double, n = _cm_points(pts)
+        opts = ModelOpts(int(bool(grid)), float(cell_size), float(cells_per_point), int(max_cells), int(shuffle_seed))
+        h = C.c_void_p()
+        L.check(lib.pcreg_model_create(a.ctypes.data_as(C.c_void_p), is_double, n, n, C.byref(opts), C.byref(h)),
+                "pcreg_model_create")
+        self._h = h
+        self.n = n
+        self.has_grid = bool(grid)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise PcregError("model handle already destroyed")
+        return self._h
+
+    def grid_info(self):
+        dims = (C.c_int32 * 3)()
+        cell = C.c_double()
+        occ = C.c_int64()
+        L.check(L.lib().pcreg_model_grid_info(self.handle, dims, C.byref(cell), C.byref(occ)), "pcreg_model_grid_info")
+        return dict(dims=tuple(dims), cell_size=cell.value, occupied=occ.value)
+
+    def nn_search(self, q, nn: int = NN_BRUTE):
+        """knnsearch(model, q, 'K', 1): returns (idx int32 [nq] 0-based, d2 float64 [nq] squared distance)."""
+        a, is_double, nq = _cm_points(q)
+        idx = np.empty(nq, dtype=np.int32)
+        d2 = np.empty(nq, dtype=np.float64)
+        L.check(L.lib().pcreg_nn_search(self.handle, a.ctypes.data_as(C.c_void_p), is_double, nq, nq, int(nn),
+                                        _ptr(idx, L.c_i32p), _ptr(d2, L.c_f64p)), "pcreg_nn_search")
+        return idx, d2
+
+    def destroy(self):
+        if self._h is not None:
+            L.lib().pcreg_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# AlignPoints family
+# ------------------------------------------------------------------------------------------------
+def align_points_batch(kind: int, pts_list, k_frac=0.85, k_abs=500, R_w=3.5, r_local=2.0, min_local=25,
+                       C1=False, C2=False):
+    """Batched AlignPoints*: list of N_b x 3 arrays (one class) -> list of
+    (pts_aligned | None, coeff_unambig | None, c) per neighbourhood."""
+    arrs = [np.asarray(p) for p in pts_list]
+    single = all(a.dtype == np.float32 for a in arrs)
+    dt = np.float32 if single else np.float64
+    sizes = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+    offsets = np.zeros(len(arrs) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    ntotal = int(offsets[-1])
+    cat = np.asfortranarray(np.concatenate([a.astype(dt, copy=False).reshape(-1, 3) for a in arrs], axis=0)) \
+        if ntotal else np.zeros((0, 3), dtype=dt, order="F")
+    out = np.zeros_like(cat, order="F")
+    nb = len(arrs)
+    coeff = np.empty((nb, 9), dtype=np.float64)
+    c3 = np.empty((nb, 3), dtype=np.float64)
+    status = np.empty(nb, dtype=np.int32)
+    o = AlignOpts(float(k_frac), int(k_abs), float(R_w), float(r_local), int(min_local), int(bool(C1)), int(bool(C2)))
+    ld = max(ntotal, 1)
+    L.check(L.lib().pcreg_align_points(int(kind), cat.ctypes.data_as(C.c_void_p), int(not single), ld if ntotal else ld,
+                                       _ptr(offsets, L.c_i64p), nb, C.byref(o), out.ctypes.data_as(C.c_void_p),
+                                       _ptr(coeff, L.c_f64p), _ptr(c3, L.c_f64p), _ptr(status, L.c_i32p)),
+            "pcreg_align_points")
+    res = []
+    for b in range(nb):
+        if status[b] != 0:
+            res.append((None, None, c3[b].copy()))
+        else:
+            res.append((np.ascontiguousarray(out[offsets[b]:offsets[b + 1]]), coeff[b].reshape(3, 3).T.copy(), c3[b].copy()))
+    return res
+
+
+def AlignPoints(pts):
+    """AlignPoints.m:1-29 -> (pts_aligned, coeff_unambig)."""
+    a, cu, _ = align_points_batch(ALIGN_PLAIN, [pts])[0]
+    return a, cu
+
+
+def AlignPoints_KNN(pts, *varargin):
+    """AlignPoints_KNN.m:1-60 -> (pts_aligned, coeff_unambig, c); optional (C1, C2) as in the reference."""
+    C1, C2 = (bool(varargin[0]), bool(varargin[1])) if len(varargin) == 2 else (False, False)
+    return align_points_batch(ALIGN_KNN_FRAC, [pts], C1=C1, C2=C2)[0]
+
+
+def AlignPoints_knn(pts, K):
+    """AlignPoints_knn.m:1-43 -> (pts_aligned, coeff_unambig, c)."""
+    return align_points_batch(ALIGN_KNN_ABS, [pts], k_abs=int(K))[0]
+
+
+def AlignPoints_weighted(pts):
+    """AlignPoints_weighted.m:1-49 -> (pts_aligned, coeff_unambig, c)."""
+    return align_points_batch(ALIGN_WEIGHTED, [pts])[0]
+
+
+def AlignPoints_c(pts):
+    """AlignPoints_c.m:1-44 -> (pts_aligned | None, coeff_unambig | None) ([] in the reference -> None)."""
+    a, cu, _ = align_points_batch(ALIGN_C, [pts])[0]
+    return a, cu
+
+
+def AlignPoints_KNN_c(pts):
+    """AlignPoints_KNN_c.m:1-57 -> (pts_aligned | None, coeff_unambig | None, c)."""
+    return align_points_batch(ALIGN_KNN_C, [pts])[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# estimateTransform / ransac
+# ------------------------------------------------------------------------------------------------
+def estimate_transform_batch(pts1_list, pts2_list, weights_list=None, reflection_fix=False):
+    """Batched estimateTransform.m: returns (T [B,4,4] with NaN where degenerate, status [B])."""
+    nb = len(pts1_list)
+    sizes = np.array([np.asarray(p).shape[0] for p in pts1_list], dtype=np.int64)
+    offsets = np.zeros(nb + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    nt = int(offsets[-1])
+    p1 = np.asfortranarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in pts1_list], axis=0))
+    p2 = np.asfortranarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in pts2_list], axis=0))
+    if p1.shape != p2.shape:
+        raise ValueError("pts1 and pts2 must have the same shapes")
+    w = None
+    if weights_list is not None:
+        w = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in weights_list]))
+    T = np.empty((nb, 16), dtype=np.float64)
+    st = np.empty(nb, dtype=np.int32)
+    L.check(L.lib().pcreg_kabsch_batch(_ptr(p1, L.c_f64p), _ptr(p2, L.c_f64p), _ptr(w, L.c_f64p), max(nt, 1),
+                                       _ptr(offsets, L.c_i64p), nb, int(bool(reflection_fix)), _ptr(T, L.c_f64p),
+                                       _ptr(st, L.c_i32p)), "pcreg_kabsch_batch")
+    return _T_from_abi(T, nb), st
+
+
+def estimateTransform(pts1, pts2, reflection_fix=False):
+    """estimateTransform.m:2-74 -> T (4x4, [pts2,1] @ T = [pts1,1]) or None where the reference returns []."""
+    T, st = estimate_transform_batch([pts1], [pts2], None, reflection_fix)
+    return None if st[0] != 0 else T[0]
+
+
+def ransac(pts1, pts2, coef: dict, triplets, reflection_fix=False, return_all=False):
+    """ransac.m:21-116 with the sample triplets supplied (0-based [iterNum, 3]).
+
+    coef: dict with thDist (SQUARED distance threshold), thInlrRatio, REFINE.  Returns a dict with the
+    reference's five outputs (T, inlierIdx, numSuccess, maxInliers, pct) plus per-hypothesis counts;
+    T is None where the reference returns []."""
+    p1 = np.asfortranarray(np.asarray(pts1, dtype=np.float64))
+    p2 = np.asfortranarray(np.asarray(pts2, dtype=np.float64))
+    P = p1.shape[0]
+    tri = np.ascontiguousarray(np.asarray(triplets, dtype=np.int32).reshape(-1, 3))
+    nh = tri.shape[0]
+    o = RansacOpts(float(coef["thDist"]), float(coef["thInlrRatio"]), int(bool(coef.get("REFINE", True))), int(bool(reflection_fix)))
+    Tb = np.empty(16, dtype=np.float64)
+    inl = np.empty(P, dtype=np.int32)
+    n_inl, n_succ, max_inl, best = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    cnt = np.empty(nh, dtype=np.int32)
+    cntr = np.empty(nh, dtype=np.int32)
+    Tall = np.empty((nh, 16), dtype=np.float64) if return_all else None
+    rc = L.check(L.lib().pcreg_ransac_score(_ptr(p1, L.c_f64p), _ptr(p2, L.c_f64p), P, P, _ptr(tri, L.c_i32p), nh,
+                                            C.byref(o), _ptr(Tb, L.c_f64p), _ptr(inl, L.c_i32p), C.byref(n_inl),
+                                            C.byref(n_succ), C.byref(max_inl), C.byref(best), _ptr(cnt, L.c_i32p),
+                                            _ptr(cntr, L.c_i32p), _ptr(Tall, L.c_f64p)), "pcreg_ransac_score")
+    out = dict(inlrNum=cnt, inlrNum_refined=cntr)
+    if return_all:
+        out["T_all"] = _T_from_abi(Tall, nh)
+    if rc != 0:
+        out.update(T=None, inlierIdx=np.zeros(0, dtype=np.int64), numSuccess=0, maxInliers=0, pct=0.0, best=-1)
+    else:
+        out.update(T=_T_from_abi(Tb), inlierIdx=inl[:n_inl.value].astype(np.int64), numSuccess=int(n_succ.value),
+                   maxInliers=int(max_inl.value), pct=100.0 * max_inl.value / P, best=int(best.value))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# batched ICP
+# ------------------------------------------------------------------------------------------------
+def icp_opts(mode=ICP_PLAIN, iters=50, k_frac=0.85, R_w=3.5, thDist2=0.0, nn=NN_BRUTE, reflection_fix=False) -> IcpOpts:
+    return IcpOpts(int(mode), int(iters), float(k_frac), float(R_w), float(thDist2), int(nn), int(bool(reflection_fix)))
+
+
+def icp_batch(model: Model, src, T0s, mode=ICP_PLAIN, iters=50, k_frac=0.85, R_w=3.5, thDist2=0.0, w_src=None,
+              nn=NN_BRUTE, reflection_fix=False, return_idx=False, return_hist=False):
+    """Multi-start ICP of `src` against the resident `model` from the initial poses T0s [H,4,4].
+    Returns dict(T [H,4,4], rmse [H], n_used [H], status [H], best, idx [H,ns]?, rmse_hist [H,iters+1]?)."""
+    a, is_double, ns = _cm_points(src)
+    T0 = _T_to_abi(np.asarray(T0s, dtype=np.float64).reshape(-1, 4, 4))
+    H = T0.shape[0]
+    o = icp_opts(mode, iters, k_frac, R_w, thDist2, nn, reflection_fix)
+    w = None if w_src is None else np.ascontiguousarray(np.asarray(w_src, dtype=np.float64).reshape(ns))
+    T = np.empty((H, 16), dtype=np.float64)
+    rmse = np.empty(H, dtype=np.float64)
+    n_used = np.empty(H, dtype=np.int32)
+    status = np.empty(H, dtype=np.int32)
+    idx = np.empty((H, ns), dtype=np.int32) if return_idx else None
+    hist = np.empty((H, iters + 1), dtype=np.float64) if return_hist else None
+    best = C.c_int64()
+    L.check(L.lib().pcreg_icp_batch(model.handle, a.ctypes.data_as(C.c_void_p), is_double, ns, ns, _ptr(w, L.c_f64p),
+                                    _ptr(T0, L.c_f64p), H, C.byref(o), _ptr(T, L.c_f64p), _ptr(rmse, L.c_f64p),
+                                    _ptr(n_used, L.c_i32p), _ptr(status, L.c_i32p), _ptr(idx, L.c_i32p),
+                                    _ptr(hist, L.c_f64p), C.byref(best)), "pcreg_icp_batch")
+    out = dict(T=_T_from_abi(T, H), rmse=rmse, n_used=n_used, status=status, best=int(best.value))
+    if return_idx:
+        out["idx"] = idx
+    if return_hist:
+        out["rmse_hist"] = hist
+    return out
+
+
+def set_profiling(enabled: bool):
+    L.check(L.lib().pcreg_set_profiling(int(bool(enabled))), "pcreg_set_profiling")
+
+
+def last_profile() -> dict:
+    buf = (C.c_double * 16)()
+    L.check(L.lib().pcreg_last_profile(buf), "pcreg_last_profile")
+    v = list(buf)
+    return dict(nn_launches=v[0], nn_ms=v[1], nn_queries=v[2], brute_pairs=v[3], update_launches=v[4],
+                update_ms=v[5], correspondences=v[6], grid_points_visited=v[7], grid_cells_visited=v[8],
+                grid_nodes_popped=v[9])
+
+
+def launch_count() -> int:
+    return int(L.load().pcreg_launch_count())

@@ -1,0 +1,411 @@
+// icp.cu -- the batched ICP loop: (NN) -> select / weight -> 17 FP64 sums -> Kabsch SVD -> pose
+// compose, for a batch of independent hypotheses, plus the C-ABI entry points pcreg_icp_batch,
+// pcreg_icp_batch_dev and pcreg_nn_search.
+//
+// Composition restated from the reference's primitives (oracle/icp.py):
+//   pose apply    quickTF.m:5-7
+//   rejection     squared-distance compare (ransac.m:49: dist < thDist keeps)
+//   trimming      keep round(k_frac * n) smallest residuals, stable sort  (AlignPoints_KNN.m:20-26)
+//   weights       w = max(R_w - r, 0)                                      (AlignPoints_weighted.m:16-18)
+//   rigid fit     estimateTransform.m:41-71 as estimateTransform(pts1 = model_j, pts2 = q)
+//   compose       T <- T * dT (row-vector convention)
+//   winner        first-index arg-min of rmse (ransac.m:69-73 tie rule mirrored)
+#include <math.h>
+#include <float.h>
+#include <algorithm>
+#include <vector>
+
+#include "pcreg_internal.h"
+#include "pcreg_dev.cuh"
+#include "pcreg_math.cuh"
+
+namespace pcreg {
+
+constexpr int UPD_THREADS = 512;
+
+// One block per hypothesis.
+__global__ void __launch_bounds__(UPD_THREADS) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
+    __shared__ double Ts[16];
+    __shared__ double red[KABSCH_NSUMS * 32];
+    __shared__ long long redll[32];
+    __shared__ RadixSelShared rsel;
+
+    const int64_t h = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t ns = a.ns;
+    if (tid < 16) Ts[tid] = a.T[h * 16 + tid];
+    __syncthreads();
+    const int32_t* __restrict__ idx = a.idx + h * ns;
+    const double* __restrict__ d2 = a.d2 + h * ns;
+    const bool reject = a.thDist2 > 0.0;
+
+    unsigned long long vK = 0ull;
+    bool all_eq = false;
+    if (a.mode == PCREG_ICP_KNN) {
+        unsigned long long* __restrict__ keys = a.keys + h * ns;
+        long long nkept = 0;
+        for (int64_t i = tid; i < ns; i += UPD_THREADS) {
+            const double d = d2[i];
+            const bool keep = idx[i] >= 0 && (!reject || d < a.thDist2);
+            keys[i] = keep ? dbits(__dsqrt_rn(d)) : KEY_NOSEL;
+            nkept += keep ? 1 : 0;
+        }
+        nkept = block_sum_ll(nkept, redll);
+        long long K = (long long)floor(a.k_frac * (double)nkept + 0.5);     // MATLAB round (AlignPoints_KNN.m:21)
+        if (K > nkept) K = nkept;
+        block_radix_select(keys, ns, K, rsel, vK, all_eq);
+    }
+
+    // ---- weights + the 17 sums ----
+    double s[KABSCH_NSUMS];
+#pragma unroll
+    for (int k = 0; k < KABSCH_NSUMS; ++k) s[k] = 0.0;
+    long long n_used = 0;
+    const double px = a.pivot[0], py = a.pivot[1], pz = a.pivot[2];
+    for (int64_t i = tid; i < ns; i += UPD_THREADS) {
+        const int32_t j = idx[i];
+        if (j < 0) continue;
+        const double d = d2[i];
+        const bool keep = !reject || d < a.thDist2;
+        double w = 0.0;
+        if (a.mode == PCREG_ICP_PLAIN) {
+            w = keep ? 1.0 : 0.0;
+        } else if (a.mode == PCREG_ICP_KNN) {
+            const unsigned long long key = a.keys[h * ns + i];
+            w = key_selected(key, vK, all_eq) ? 1.0 : 0.0;
+        } else {
+            if (keep) {
+                const double r = __dsqrt_rn(d);
+                w = fmax(__dsub_rn(a.R_w, r), 0.0);
+            }
+        }
+        if (a.w_src) w = __dmul_rn(w, a.w_src[i]);
+        if (w > 0.0) ++n_used;
+        if (w != 0.0) {
+            double qx, qy, qz;
+            quick_tf(Ts, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
+            const ModelPointD m = a.md[j];
+            const double q0 = qx - px, q1 = qy - py, q2 = qz - pz;
+            const double m0 = m.x - px, m1 = m.y - py, m2 = m.z - pz;
+            const double wq0 = w * q0, wq1 = w * q1, wq2 = w * q2;
+            s[0] += w;
+            s[1] += wq0; s[2] += wq1; s[3] += wq2;
+            s[4] += w * m0; s[5] += w * m1; s[6] += w * m2;
+            s[7] += wq0 * m0; s[8] += wq0 * m1; s[9] += wq0 * m2;
+            s[10] += wq1 * m0; s[11] += wq1 * m1; s[12] += wq1 * m2;
+            s[13] += wq2 * m0; s[14] += wq2 * m1; s[15] += wq2 * m2;
+            s[16] += w * d;
+        }
+    }
+    block_sum<KABSCH_NSUMS>(s, red);
+    n_used = block_sum_ll(n_used, redll);
+
+    if (tid == 0) {
+        const double sw = s[0];
+        const double rmse = (sw > 0.0) ? sqrt(s[16] / sw) : nan("");
+        a.rmse[h] = rmse;
+        a.n_used[h] = (int32_t)n_used;
+        if (a.rmse_hist) a.rmse_hist[h * a.hist_stride + a.hist_col] = rmse;
+        if (a.update && !a.frozen[h]) {
+            if (n_used < 3 || !(sw > 0.0)) {
+                a.frozen[h] = 1;
+            } else {
+                KabschSums ks;
+                ks.sw = sw;
+                for (int k = 0; k < 3; ++k) { ks.sq[k] = s[1 + k]; ks.sm[k] = s[4 + k]; }
+                for (int k = 0; k < 9; ++k) ks.sqm[k] = s[7 + k];
+                ks.swd2 = s[16];
+                double dT[16], Tn[16], Tc[16];
+                kabsch_from_sums(ks, a.pivot, a.pivot, a.reflection_fix != 0, dT);
+                for (int k = 0; k < 16; ++k) Tc[k] = Ts[k];
+                mul4(Tc, dT, Tn);
+                for (int k = 0; k < 16; ++k) a.T[h * 16 + k] = Tn[k];
+            }
+        }
+    }
+}
+
+// first-index arg-min over hypotheses, NaN never wins; one block.
+__global__ void __launch_bounds__(1024) k_icp_argmin(const double* __restrict__ rmse, int64_t n, int64_t* __restrict__ best) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    double bv = INFINITY;
+    long long bi = -1;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = rmse[i];
+        if (v == v && (bi < 0 || v < bv)) { bv = v; bi = i; }     // strided scan keeps the lowest index per thread on ties
+    }
+    auto better = [](double v, long long i, double ov, long long oi) {
+        if (oi < 0) return false;
+        if (i < 0) return true;
+        return ov < v || (ov == v && oi < i);
+    };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(bv, bi, ov, oi)) { bv = ov; bi = oi; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        bv = lane < nw ? sv[lane] : INFINITY;
+        bi = lane < nw ? si[lane] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(bv, bi, ov, oi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) *best = bi;
+    }
+}
+
+// MATLAB column-major 4x4 <-> internal row-major 4x4 (a transpose), batched
+__global__ void k_transpose16(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * 16) return;
+    const int64_t h = g >> 4;
+    const int e = (int)(g & 15), r = e >> 2, c = e & 3;
+    out[h * 16 + r * 4 + c] = in[h * 16 + c * 4 + r];
+}
+
+void transpose16_launch(const double* d_in, double* d_out, int64_t n, cudaStream_t st) {
+    k_transpose16<<<(unsigned)((n * 16 + 255) / 256), 256, 0, st>>>(d_in, d_out, n);
+    PCREG_LAUNCHED();
+}
+void icp_update_launch(const IcpUpdateArgs& a, int64_t nhyp, cudaStream_t st) {
+    k_icp_update<<<(unsigned)nhyp, UPD_THREADS, 0, st>>>(a);
+    PCREG_LAUNCHED();
+}
+void icp_argmin_launch(const double* d_rmse, int64_t nhyp, int64_t* d_best, cudaStream_t st) {
+    k_icp_argmin<<<1, 1024, 0, st>>>(d_rmse, nhyp, d_best);
+    PCREG_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+struct EventPair { cudaEvent_t a, b; int kind; };
+
+static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3, ld = ns*/, int64_t ns,
+                    const double* d_w, const double* d_T0_cm, int64_t nhyp, const pcreg_icp_opts& o,
+                    double* d_T16_cm, double* d_rmse, int32_t* d_n_used, int32_t* d_status, int32_t* d_idx,
+                    double* d_rmse_hist, int64_t* d_best, cudaStream_t st) {
+    PCREG_REQUIRE(m && d_src && d_T0_cm && d_T16_cm, "icp: null pointer");
+    PCREG_REQUIRE(ns >= 1 && nhyp >= 1, "icp: need ns >= 1 and nhyp >= 1");
+    PCREG_REQUIRE(o.iters >= 0, "icp: iters must be >= 0");
+    PCREG_REQUIRE(o.mode >= PCREG_ICP_PLAIN && o.mode <= PCREG_ICP_WEIGHTED, "icp: bad mode");
+    PCREG_REQUIRE(o.nn == PCREG_NN_BRUTE || o.nn == PCREG_NN_GRID, "icp: bad nn kind");
+    if (o.nn == PCREG_NN_GRID) PCREG_REQUIRE(m->has_grid, "icp: grid NN requested but the model has no grid");
+    Context& c = ctx();
+    const bool prof = c.profiling;
+    for (int i = 0; i < 16; ++i) c.profile[i] = 0.0;
+
+    // chunk the hypotheses so that the per-correspondence scratch stays bounded
+    const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0));
+    const size_t budget = (size_t)3 << 30;
+    int64_t hc = (int64_t)std::max<size_t>(1, budget / per_hyp);
+    hc = std::min(hc, nhyp);
+    hc = std::min<int64_t>(hc, 2147483647LL / std::max<int64_t>(1, ns) );       // int32 grid.x of per-query kernels stays safe
+    hc = std::max<int64_t>(hc, 1);
+
+    DevBuf<double> Twork((size_t)nhyp * 16);
+    DevBuf<int32_t> idxA((size_t)hc * ns), idxB((size_t)hc * ns);
+    DevBuf<double> d2((size_t)hc * ns);
+    DevBuf<unsigned long long> keys(o.mode == PCREG_ICP_KNN ? (size_t)hc * ns : 0);
+    DevBuf<int32_t> frozen((size_t)nhyp);
+    DevBuf<double> rmse_tmp(d_rmse ? 0 : (size_t)nhyp);
+    DevBuf<int32_t> nused_tmp(d_n_used ? 0 : (size_t)nhyp);
+    DevBuf<unsigned long long> counters(3);
+    NNScratch scratch;
+    double* rm = d_rmse ? d_rmse : rmse_tmp.p;
+    int32_t* nu = d_n_used ? d_n_used : nused_tmp.p;
+
+    PCREG_CUDA(cudaMemsetAsync(frozen.p, 0, frozen.bytes(), st));
+    PCREG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
+    transpose16_launch(d_T0_cm, Twork.p, nhyp, st);
+
+    std::vector<EventPair> evs;
+    auto ev_begin = [&](int kind) {
+        if (!prof) return;
+        EventPair e; e.kind = kind;
+        PCREG_CUDA(cudaEventCreate(&e.a)); PCREG_CUDA(cudaEventCreate(&e.b));
+        PCREG_CUDA(cudaEventRecord(e.a, st));
+        evs.push_back(e);
+    };
+    auto ev_end = [&]() { if (prof) PCREG_CUDA(cudaEventRecord(evs.back().b, st)); };
+
+    const double* sx = d_src; const double* sy = d_src + ns; const double* sz = d_src + 2 * ns;
+    double nn_launches = 0, upd_launches = 0;
+    for (int64_t h0 = 0; h0 < nhyp; h0 += hc) {
+        const int64_t hn = std::min(hc, nhyp - h0);
+        int32_t* cur = idxA.p; int32_t* prev = idxB.p;
+        bool have_prev = false;
+        for (int it = 0; it <= o.iters; ++it) {
+            const bool last = (it == o.iters);
+            int32_t* out_idx = (last && d_idx) ? d_idx + h0 * ns : cur;
+            ev_begin(0);
+            if (o.nn == PCREG_NN_BRUTE)
+                nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p, scratch, st);
+            else
+                nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p,
+                               prof ? counters.p : nullptr, st);
+            ev_end();
+            nn_launches += 1;
+            IcpUpdateArgs ua{};
+            ua.md = m->md.p;
+            for (int k = 0; k < 3; ++k) ua.pivot[k] = m->pivot[k];
+            ua.sx = sx; ua.sy = sy; ua.sz = sz; ua.w_src = d_w; ua.ns = ns;
+            ua.T = Twork.p + h0 * 16; ua.idx = out_idx; ua.d2 = d2.p; ua.keys = keys.p;
+            ua.mode = o.mode; ua.k_frac = o.k_frac; ua.R_w = o.R_w; ua.thDist2 = o.thDist2; ua.reflection_fix = o.reflection_fix;
+            ua.update = last ? 0 : 1;
+            ua.frozen = frozen.p + h0; ua.rmse = rm + h0; ua.n_used = nu + h0;
+            ua.rmse_hist = d_rmse_hist ? d_rmse_hist + h0 * (o.iters + 1) : nullptr;
+            ua.hist_stride = o.iters + 1; ua.hist_col = it;
+            ev_begin(1);
+            icp_update_launch(ua, hn, st);
+            ev_end();
+            upd_launches += 1;
+            std::swap(cur, prev);       // what was just written becomes the warm start
+            have_prev = true;
+        }
+    }
+    transpose16_launch(Twork.p, d_T16_cm, nhyp, st);
+    if (d_status) PCREG_CUDA(cudaMemcpyAsync(d_status, frozen.p, (size_t)nhyp * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (d_best) icp_argmin_launch(rm, nhyp, d_best, st);
+
+    // scratch is freed when this function returns: the stream must have drained
+    PCREG_CUDA(cudaStreamSynchronize(st));
+    if (prof) {
+        double nn_ms = 0, upd_ms = 0;
+        for (auto& e : evs) {
+            float ms = 0.f;
+            PCREG_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+            (e.kind == 0 ? nn_ms : upd_ms) += ms;
+            cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+        }
+        unsigned long long hcnt[3] = {0, 0, 0};
+        PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
+        const double nq = (double)nhyp * (double)ns * (double)(o.iters + 1);
+        c.profile[0] = nn_launches; c.profile[1] = nn_ms; c.profile[2] = nq;
+        c.profile[3] = (o.nn == PCREG_NN_BRUTE) ? nq * (double)m->n : 0.0;
+        c.profile[4] = upd_launches; c.profile[5] = upd_ms; c.profile[6] = nq;
+        c.profile[7] = (double)hcnt[0]; c.profile[8] = (double)hcnt[1]; c.profile[9] = (double)hcnt[2];
+    }
+}
+
+// host column-major (float or double, ld) -> contiguous double column-major ns x 3
+static std::vector<double> to_double_cm(const void* p, int is_double, int64_t n, int64_t ld) {
+    std::vector<double> out((size_t)n * 3);
+    for (int a = 0; a < 3; ++a)
+        for (int64_t i = 0; i < n; ++i)
+            out[(size_t)a * n + i] = is_double ? ((const double*)p)[a * ld + i] : (double)((const float*)p)[a * ld + i];
+    return out;
+}
+
+}  // namespace pcreg
+
+using namespace pcreg;
+
+extern "C" {
+
+void pcreg_icp_opts_default(pcreg_icp_opts* o) {
+    if (!o) return;
+    o->mode = PCREG_ICP_PLAIN; o->iters = 50; o->k_frac = 0.85; o->R_w = 3.5; o->thDist2 = 0.0;
+    o->nn = PCREG_NN_BRUTE; o->reflection_fix = 0;
+}
+
+int pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns, const double* d_w_src,
+                        const double* d_T0_16, int64_t nhyp, const pcreg_icp_opts* opts, double* d_T16,
+                        double* d_rmse, int32_t* d_n_used, int32_t* d_status, int32_t* d_idx, double* d_rmse_hist,
+                        int64_t* d_best, void* stream) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(opts, "pcreg_icp_batch_dev: opts is null");
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    icp_run(m, d_src, ns, d_w_src, d_T0_16, nhyp, *opts, d_T16, d_rmse, d_n_used, d_status, d_idx, d_rmse_hist,
+            d_best, (cudaStream_t)stream);
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+int pcreg_icp_batch(const pcreg_model* m, const void* src, int is_double, int64_t ns, int64_t ld, const double* w_src,
+                    const double* T0_16, int64_t nhyp, const pcreg_icp_opts* opts, double* T16, double* rmse,
+                    int32_t* n_used, int32_t* status, int32_t* idx, double* rmse_hist, int64_t* best) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(m && src && T0_16 && T16 && opts, "pcreg_icp_batch: null pointer");
+    PCREG_REQUIRE(ns >= 1 && ld >= ns && nhyp >= 1, "pcreg_icp_batch: bad sizes");
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    cudaStream_t st = 0;
+    std::vector<double> hs = to_double_cm(src, is_double, ns, ld);
+    DevBuf<double> d_src((size_t)ns * 3), d_w(w_src ? (size_t)ns : 0), d_T0((size_t)nhyp * 16), d_T((size_t)nhyp * 16);
+    DevBuf<double> d_rmse((size_t)nhyp), d_hist(rmse_hist ? (size_t)nhyp * (opts->iters + 1) : 0);
+    DevBuf<int32_t> d_nu((size_t)nhyp), d_st((size_t)nhyp), d_idx(idx ? (size_t)nhyp * ns : 0);
+    DevBuf<int64_t> d_best(1);
+    PCREG_CUDA(cudaMemcpyAsync(d_src.p, hs.data(), d_src.bytes(), cudaMemcpyHostToDevice, st));
+    if (w_src) PCREG_CUDA(cudaMemcpyAsync(d_w.p, w_src, d_w.bytes(), cudaMemcpyHostToDevice, st));
+    PCREG_CUDA(cudaMemcpyAsync(d_T0.p, T0_16, d_T0.bytes(), cudaMemcpyHostToDevice, st));
+    icp_run(m, d_src.p, ns, w_src ? d_w.p : nullptr, d_T0.p, nhyp, *opts, d_T.p, d_rmse.p, d_nu.p, d_st.p,
+            idx ? d_idx.p : nullptr, rmse_hist ? d_hist.p : nullptr, d_best.p, st);
+    PCREG_CUDA(cudaMemcpyAsync(T16, d_T.p, d_T.bytes(), cudaMemcpyDeviceToHost, st));
+    if (rmse) PCREG_CUDA(cudaMemcpyAsync(rmse, d_rmse.p, d_rmse.bytes(), cudaMemcpyDeviceToHost, st));
+    if (n_used) PCREG_CUDA(cudaMemcpyAsync(n_used, d_nu.p, d_nu.bytes(), cudaMemcpyDeviceToHost, st));
+    if (status) PCREG_CUDA(cudaMemcpyAsync(status, d_st.p, d_st.bytes(), cudaMemcpyDeviceToHost, st));
+    if (idx) PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
+    if (rmse_hist) PCREG_CUDA(cudaMemcpyAsync(rmse_hist, d_hist.p, d_hist.bytes(), cudaMemcpyDeviceToHost, st));
+    if (best) PCREG_CUDA(cudaMemcpyAsync(best, d_best.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t nq, int64_t ld, int nn_kind,
+                    int32_t* idx, double* d2) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(m && q && idx, "pcreg_nn_search: null pointer");
+    PCREG_REQUIRE(nq >= 1 && ld >= nq, "pcreg_nn_search: bad sizes");
+    PCREG_REQUIRE(nn_kind == PCREG_NN_BRUTE || nn_kind == PCREG_NN_GRID, "pcreg_nn_search: bad nn kind");
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    cudaStream_t st = 0;
+    Context& c = ctx();
+    for (int i = 0; i < 16; ++i) c.profile[i] = 0.0;
+    std::vector<double> hq = to_double_cm(q, is_double, nq, ld);
+    const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    DevBuf<double> d_q((size_t)nq * 3), d_T(16), d_d2((size_t)nq);
+    DevBuf<int32_t> d_idx((size_t)nq);
+    DevBuf<unsigned long long> counters(3);
+    NNScratch scratch;
+    PCREG_CUDA(cudaMemcpyAsync(d_q.p, hq.data(), d_q.bytes(), cudaMemcpyHostToDevice, st));
+    PCREG_CUDA(cudaMemcpyAsync(d_T.p, I16, sizeof I16, cudaMemcpyHostToDevice, st));
+    PCREG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c.profiling) { PCREG_CUDA(cudaEventCreate(&e0)); PCREG_CUDA(cudaEventCreate(&e1)); PCREG_CUDA(cudaEventRecord(e0, st)); }
+    if (nn_kind == PCREG_NN_BRUTE)
+        nn_brute_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p, scratch, st);
+    else
+        nn_grid_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p,
+                       c.profiling ? counters.p : nullptr, st);
+    if (c.profiling) PCREG_CUDA(cudaEventRecord(e1, st));
+    PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
+    if (d2) PCREG_CUDA(cudaMemcpyAsync(d2, d_d2.p, d_d2.bytes(), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));
+    if (c.profiling) {
+        float ms = 0.f;
+        PCREG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        unsigned long long hcnt[3] = {0, 0, 0};
+        PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
+        c.profile[0] = 1; c.profile[1] = ms; c.profile[2] = (double)nq;
+        c.profile[3] = nn_kind == PCREG_NN_BRUTE ? (double)nq * (double)m->n : 0.0;
+        c.profile[7] = (double)hcnt[0]; c.profile[8] = (double)hcnt[1]; c.profile[9] = (double)hcnt[2];
+    }
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+}  // extern "C"

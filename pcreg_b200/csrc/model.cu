@@ -1,0 +1,396 @@
+// model.cu -- library context, error state, the GPU-resident model cloud handle and the
+// on-device uniform-grid build (hand-written counting sort + occupancy pyramid).
+//
+// Reference context: every driver loads one dense model cloud and reuses it for thousands of
+// alignments (completeExperiment.m:15, slideMatchingWindow_v2.m:15, class single as written by
+// upsampleMesh.m:21); the handle makes that cloud resident in HBM once.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <atomic>
+#include <algorithm>
+
+#include "pcreg_internal.h"
+#include "pcreg_dev.cuh"
+
+namespace pcreg {
+
+static thread_local char g_err[1024] = "";
+static char g_err_global[1024] = "";
+static std::atomic<long long> g_launches{0};
+static Context g_ctx;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    memcpy(g_err_global, g_err, sizeof g_err);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+Context& ctx() { return g_ctx; }
+void require_init() {
+    if (!g_ctx.initialised) throw ArgError{"pcreg_init has not been called (or failed): no CUDA device, and there is no CPU fallback"};
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// scan-order float4 array: (x,y,z) relative to the pivot rounded to FP32, w = |.|^2 of the ROUNDED
+// coordinates (computed in FP64, rounded once).  Padding entries are far-away sentinels.
+__global__ void k_build_m4(const ModelPointD* __restrict__ md, const int32_t* __restrict__ perm, int64_t n,
+                           int64_t n_pad, double px, double py, double pz, float4* __restrict__ m4) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pad) return;
+    float4 o;
+    if (j < n) {
+        const ModelPointD p = md[perm[j]];
+        o.x = __double2float_rn(p.x - px);
+        o.y = __double2float_rn(p.y - py);
+        o.z = __double2float_rn(p.z - pz);
+        o.w = __double2float_rn((double)o.x * (double)o.x + (double)o.y * (double)o.y + (double)o.z * (double)o.z);
+    } else {
+        o.x = 1.0e18f; o.y = 1.0e18f; o.z = 1.0e18f; o.w = 3.0e36f;
+    }
+    m4[j] = o;
+}
+
+__device__ __forceinline__ int cell_coord(double v, double origin, double inv_cell, int dim) {
+    int c = (int)floor((v - origin) * inv_cell);
+    return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+}
+
+__global__ void k_grid_count(const ModelPointD* __restrict__ md, int64_t n, GridView g, int32_t* __restrict__ cell_of,
+                             int32_t* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ModelPointD p = md[i];
+    const int cx = cell_coord(p.x, g.origin[0], g.inv_cell, g.dims[0][0]);
+    const int cy = cell_coord(p.y, g.origin[1], g.inv_cell, g.dims[0][1]);
+    const int cz = cell_coord(p.z, g.origin[2], g.inv_cell, g.dims[0][2]);
+    const int32_t c = (cz * g.dims[0][1] + cy) * g.dims[0][0] + cx;
+    cell_of[i] = c;
+    atomicAdd(&count[c], 1);
+}
+
+// --- exclusive scan (three phases, hand-written) ---
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_excl_scan(int v, int* smem /*[32]*/, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = smem[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem[lane] = winc - w;               // exclusive warp offsets
+        if (lane == 31) smem[32] = winc;     // block total
+    }
+    __syncthreads();
+    const int res = inc - v + smem[warp];
+    total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+// phase 1: in-place exclusive scan of each SCAN_BLOCK chunk, chunk totals to block_sums
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(int32_t* __restrict__ data, int64_t n, int32_t* __restrict__ block_sums) {
+    __shared__ int smem[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? data[base + k] : 0; s += v[k]; }
+    int total;
+    int off = block_excl_scan(s, smem, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) data[base + k] = off; off += v[k]; }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+// phase 2: one block scans the chunk totals (in place, exclusive); grand total to *total_out
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(int32_t* __restrict__ sums, int nb, int32_t* __restrict__ total_out) {
+    __shared__ int smem[33];
+    int carry = 0;
+    for (int base = 0; base < nb; base += SCAN_THREADS) {
+        const int i = base + threadIdx.x;
+        const int v = (i < nb) ? sums[i] : 0;
+        int total;
+        const int off = block_excl_scan(v, smem, total);
+        if (i < nb) sums[i] = off + carry;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+// phase 3: add chunk offsets; also writes the terminating entry data[n] = grand total
+__global__ void k_scan_add(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ sums, const int32_t* __restrict__ total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] += sums[i / SCAN_BLOCK];
+    if (i == n) data[n] = *total;
+}
+
+__global__ void k_grid_scatter(const ModelPointD* __restrict__ md, int64_t n, const int32_t* __restrict__ cell_of,
+                               const int32_t* __restrict__ cell_start, int32_t* __restrict__ cursor,
+                               GridPoint* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = cell_of[i];
+    const int32_t pos = cell_start[c] + atomicAdd(&cursor[c], 1);
+    const ModelPointD p = md[i];
+    GridPoint gp;
+    gp.x = p.x; gp.y = p.y; gp.z = p.z; gp.orig = (int32_t)i; gp.pad = 0;
+    out[pos] = gp;
+}
+
+// occupancy pyramid: level-l mask bit (dz<<2 | dy<<1 | dx) set iff that child at level l-1 is non-empty
+__global__ void k_grid_mask(GridView g, int level, const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ below,
+                            uint8_t* __restrict__ out, unsigned long long* __restrict__ occupied0) {
+    const int dx = g.dims[level][0], dy = g.dims[level][1], dz = g.dims[level][2];
+    const int64_t total = (int64_t)dx * dy * dz;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    const int ix = (int)(c % dx), iy = (int)((c / dx) % dy), iz = (int)(c / ((int64_t)dx * dy));
+    const int bx = g.dims[level - 1][0], by = g.dims[level - 1][1], bz = g.dims[level - 1][2];
+    unsigned m = 0;
+    int occ = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int x = ix * 2 + (k & 1), y = iy * 2 + ((k >> 1) & 1), z = iz * 2 + (k >> 2);
+        if (x >= bx || y >= by || z >= bz) continue;
+        const int64_t cc = ((int64_t)z * by + y) * bx + x;
+        bool ne;
+        if (level == 1) ne = cell_start[cc + 1] > cell_start[cc];
+        else            ne = below[cc] != 0;
+        if (ne) { m |= 1u << k; ++occ; }
+    }
+    out[c] = (uint8_t)m;
+    if (level == 1 && occ) atomicAdd(occupied0, (unsigned long long)occ);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid build (host driver)
+// ------------------------------------------------------------------------------------------------
+void grid_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
+    const int64_t n = m->n;
+    GridView g{};
+    double ext[3], maxext = 0.0;
+    for (int a = 0; a < 3; ++a) { ext[a] = m->bbox_hi[a] - m->bbox_lo[a]; maxext = std::max(maxext, ext[a]); }
+    if (!(maxext > 0.0)) maxext = 1.0;
+    double cell = o.cell_size;
+    if (!(cell > 0.0)) {
+        const double cpp = o.cells_per_point > 0.0 ? o.cells_per_point : 16.0;
+        const double cap = (double)(o.max_cells > 0 ? o.max_cells : ((int64_t)1 << 27));
+        const double target = std::min(cap, std::max(64.0, cpp * (double)n));
+        double vol = 1.0;
+        for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * maxext);
+        cell = cbrt(vol / target);
+    }
+    cell = std::max(cell, maxext / 1000.0);           // at most ~1001 cells per axis (10-bit coordinates)
+    const double cap_cells = (double)(o.max_cells > 0 ? o.max_cells : ((int64_t)1 << 27));
+    for (;;) {                                        // honour the cap exactly
+        double tot = 1.0;
+        for (int a = 0; a < 3; ++a) tot *= floor(ext[a] / cell) + 1.0;
+        if (tot <= cap_cells) break;
+        cell *= 1.05;
+    }
+    g.cell = cell;
+    g.inv_cell = 1.0 / cell;
+    for (int a = 0; a < 3; ++a) {
+        g.origin[a] = m->bbox_lo[a];
+        g.dims[0][a] = (int32_t)floor(ext[a] / cell) + 1;
+    }
+    int L = 1;
+    while (!(g.dims[L - 1][0] == 1 && g.dims[L - 1][1] == 1 && g.dims[L - 1][2] == 1)) {
+        PCREG_REQUIRE(L < GRID_MAX_LEVELS, "grid: too many pyramid levels");
+        for (int a = 0; a < 3; ++a) g.dims[L][a] = (g.dims[L - 1][a] + 1) / 2;
+        ++L;
+    }
+    g.nlevels = L;
+    const int64_t ncell0 = (int64_t)g.dims[0][0] * g.dims[0][1] * g.dims[0][2];
+    PCREG_REQUIRE(ncell0 < ((int64_t)1 << 31) - 2 && n < ((int64_t)1 << 31) - 2, "grid: too many cells or points for int32 indexing");
+
+    m->g_cell_start.alloc((size_t)ncell0 + 1);
+    m->g_pts.alloc((size_t)n);
+    DevBuf<int32_t> cell_of((size_t)n), cursor((size_t)ncell0);
+    const int nb_scan = (int)((ncell0 + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    DevBuf<int32_t> sums((size_t)nb_scan + 1), total(1);
+    DevBuf<unsigned long long> occ(1);
+    PCREG_CUDA(cudaMemsetAsync(m->g_cell_start.p, 0, m->g_cell_start.bytes(), st));
+    PCREG_CUDA(cudaMemsetAsync(cursor.p, 0, cursor.bytes(), st));
+    PCREG_CUDA(cudaMemsetAsync(occ.p, 0, sizeof(unsigned long long), st));
+
+    const int T = 256;
+    k_grid_count<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(m->md.p, n, g, cell_of.p, m->g_cell_start.p);
+    PCREG_LAUNCHED();
+    k_scan_local<<<nb_scan, SCAN_THREADS, 0, st>>>(m->g_cell_start.p, ncell0, sums.p);
+    PCREG_LAUNCHED();
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(sums.p, nb_scan, total.p);
+    PCREG_LAUNCHED();
+    k_scan_add<<<(unsigned)((ncell0 + 1 + T - 1) / T), T, 0, st>>>(m->g_cell_start.p, ncell0, sums.p, total.p);
+    PCREG_LAUNCHED();
+    k_grid_scatter<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(m->md.p, n, cell_of.p, m->g_cell_start.p, cursor.p, m->g_pts.p);
+    PCREG_LAUNCHED();
+
+    g.pts = m->g_pts.p;
+    g.cell_start = m->g_cell_start.p;
+    m->g_masks.clear();
+    m->g_masks.resize(L);
+    for (int l = 0; l < GRID_MAX_LEVELS; ++l) g.mask[l] = nullptr;
+    for (int l = 1; l < L; ++l) {
+        const int64_t nc = (int64_t)g.dims[l][0] * g.dims[l][1] * g.dims[l][2];
+        m->g_masks[l].alloc((size_t)nc);
+        k_grid_mask<<<(unsigned)((nc + T - 1) / T), T, 0, st>>>(g, l, m->g_cell_start.p, l > 1 ? m->g_masks[l - 1].p : nullptr,
+                                                                m->g_masks[l].p, occ.p);
+        PCREG_LAUNCHED();
+        g.mask[l] = m->g_masks[l].p;
+    }
+    unsigned long long h_occ = 0;
+    PCREG_CUDA(cudaMemcpyAsync(&h_occ, occ.p, sizeof h_occ, cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));
+    m->g_occupied = (L > 1) ? (int64_t)h_occ : (n > 0 ? 1 : 0);
+    m->grid = g;
+    m->has_grid = true;
+}
+
+}  // namespace pcreg
+
+using namespace pcreg;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: lifetime + model handle
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pcreg_abi_version(void) { return 1; }
+const char* pcreg_last_error(void) { return g_err[0] ? g_err : g_err_global; }
+int64_t pcreg_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pcreg_init(const int* devices, int ndev) {
+    PCREG_API_BEGIN
+    PCREG_REQUIRE(ndev <= 1, "pcreg_init: one process drives one GPU (ndev must be 1); shard hypotheses across ranks");
+    const int dev = (devices && ndev == 1) ? devices[0] : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("pcreg_init: no usable CUDA device (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return PCREG_ERR_CUDA;
+    }
+    PCREG_REQUIRE(dev >= 0 && dev < count, "pcreg_init: device ordinal out of range");
+    PCREG_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp p;
+    PCREG_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (p.major < 10) {
+        set_error("pcreg_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, p.major, p.minor);
+        return PCREG_ERR_CUDA;
+    }
+    Context& c = ctx();
+    c.device = dev;
+    c.sm_count = p.multiProcessorCount;
+    c.smem_optin = p.sharedMemPerBlockOptin;
+    c.initialised = true;
+    g_launches.store(0);
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+int pcreg_shutdown(void) {
+    ctx().initialised = false;
+    return PCREG_OK;
+}
+
+int pcreg_set_profiling(int enabled) { ctx().profiling = enabled != 0; return PCREG_OK; }
+int pcreg_last_profile(double out[16]) {
+    if (!out) return PCREG_ERR_ARG;
+    for (int i = 0; i < 16; ++i) out[i] = ctx().profile[i];
+    return PCREG_OK;
+}
+
+int pcreg_model_create(const void* xyz, int is_double, int64_t n, int64_t ld, const pcreg_model_opts* opts, pcreg_model** out) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(xyz && out, "pcreg_model_create: null pointer");
+    PCREG_REQUIRE(n >= 1 && ld >= n, "pcreg_model_create: need n >= 1 and ld >= n");
+    PCREG_REQUIRE(n < ((int64_t)1 << 31) - BRUTE_TILE, "pcreg_model_create: model too large for int32 indices");
+    pcreg_model_opts o{};
+    if (opts) o = *opts;
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    std::unique_ptr<pcreg_model> m(new pcreg_model());
+    m->n = n;
+    m->n_pad = ((n + BRUTE_TILE - 1) / BRUTE_TILE) * BRUTE_TILE;
+
+    // host staging: FP64 AoS in original order, bounding box, pivot, FP32 norm bound
+    std::vector<ModelPointD> h((size_t)n);
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = 0; i < n; ++i) {
+        double v[3];
+        for (int a = 0; a < 3; ++a)
+            v[a] = is_double ? ((const double*)xyz)[a * ld + i] : (double)((const float*)xyz)[a * ld + i];
+        PCREG_REQUIRE(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]), "pcreg_model_create: non-finite model coordinate");
+        h[i].x = v[0]; h[i].y = v[1]; h[i].z = v[2]; h[i].pad = 0.0;
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], v[a]); hi[a] = std::max(hi[a], v[a]); }
+    }
+    double maxn2 = 0.0;
+    for (int a = 0; a < 3; ++a) { m->bbox_lo[a] = lo[a]; m->bbox_hi[a] = hi[a]; m->pivot[a] = 0.5 * (lo[a] + hi[a]); }
+    for (int64_t i = 0; i < n; ++i) {
+        const float x = (float)(h[i].x - m->pivot[0]), y = (float)(h[i].y - m->pivot[1]), z = (float)(h[i].z - m->pivot[2]);
+        maxn2 = std::max(maxn2, (double)x * x + (double)y * y + (double)z * z);
+    }
+    m->max_norm = (float)(sqrt(maxn2) * (1.0 + 1e-6));
+    // scan-order permutation (Fisher-Yates, splitmix64)
+    std::vector<int32_t> perm((size_t)n);
+    for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
+    uint64_t s = o.shuffle_seed + 0x9E3779B97F4A7C15ull;
+    auto next = [&s]() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+    for (int64_t i = n - 1; i > 0; --i) {
+        const int64_t j = (int64_t)(next() % (uint64_t)(i + 1));
+        std::swap(perm[i], perm[j]);
+    }
+    cudaStream_t st = 0;
+    m->md.alloc((size_t)n);
+    m->perm.alloc((size_t)m->n_pad);
+    m->m4.alloc((size_t)m->n_pad);
+    PCREG_CUDA(cudaMemcpyAsync(m->md.p, h.data(), (size_t)n * sizeof(ModelPointD), cudaMemcpyHostToDevice, st));
+    PCREG_CUDA(cudaMemsetAsync(m->perm.p, 0xff, m->perm.bytes(), st));
+    PCREG_CUDA(cudaMemcpyAsync(m->perm.p, perm.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    k_build_m4<<<(unsigned)((m->n_pad + 255) / 256), 256, 0, st>>>(m->md.p, m->perm.p, n, m->n_pad, m->pivot[0], m->pivot[1], m->pivot[2], m->m4.p);
+    PCREG_LAUNCHED();
+    if (o.build_grid) grid_build(m.get(), o, st);
+    PCREG_CUDA(cudaStreamSynchronize(st));
+    *out = m.release();
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+int pcreg_model_destroy(pcreg_model* m) {
+    PCREG_API_BEGIN
+    if (m) { cudaDeviceSynchronize(); delete m; }
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+int64_t pcreg_model_size(const pcreg_model* m) { return m ? m->n : -1; }
+
+int pcreg_model_grid_info(const pcreg_model* m, int32_t dims[3], double* cell_size, int64_t* occupied) {
+    if (!m || !m->has_grid) { set_error("pcreg_model_grid_info: model has no grid"); return PCREG_ERR_STATE; }
+    if (dims) for (int a = 0; a < 3; ++a) dims[a] = m->grid.dims[0][a];
+    if (cell_size) *cell_size = m->grid.cell;
+    if (occupied) *occupied = m->g_occupied;
+    return PCREG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// pcreg_internal.h -- host-side state shared by the translation units of libpcreg_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include <memory>
+#include <new>
+
+#include "../../include/pcreg.h"
+
+namespace pcreg {
+
+// ---- error plumbing --------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+struct CudaFail { cudaError_t e; const char* what; const char* file; int line; };
+
+#define PCREG_CUDA(call)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) throw ::pcreg::CudaFail{_e, #call, __FILE__, __LINE__};        \
+    } while (0)
+
+// Bumps the launch counter and checks the launch error (no sync).
+void count_launch(int n = 1);
+#define PCREG_LAUNCHED()                                                                      \
+    do {                                                                                      \
+        ::pcreg::count_launch();                                                              \
+        PCREG_CUDA(cudaGetLastError());                                                       \
+    } while (0)
+
+struct ArgError { std::string msg; };
+#define PCREG_REQUIRE(cond, msg)                                                              \
+    do { if (!(cond)) throw ::pcreg::ArgError{msg}; } while (0)
+
+// Every extern "C" body is wrapped in these: no C++ exception crosses the ABI.
+#define PCREG_API_BEGIN try {
+#define PCREG_API_END                                                                                         \
+    }                                                                                                         \
+    catch (const ::pcreg::CudaFail& f) {                                                                      \
+        ::pcreg::set_error("CUDA error %d (%s) in %s at %s:%d", (int)f.e, cudaGetErrorString(f.e), f.what, f.file, f.line); \
+        cudaGetLastError();                                                                                   \
+        return PCREG_ERR_CUDA;                                                                                \
+    }                                                                                                         \
+    catch (const ::pcreg::ArgError& a) { ::pcreg::set_error("%s", a.msg.c_str()); return PCREG_ERR_ARG; }     \
+    catch (const std::bad_alloc&) { ::pcreg::set_error("host allocation failed"); return PCREG_ERR_ALLOC; }   \
+    catch (...) { ::pcreg::set_error("unknown C++ exception"); return PCREG_ERR_STATE; }
+
+// ---- library context (one device per process) -------------------------------------------------
+struct Context {
+    bool initialised = false;
+    int  device = 0;
+    int  sm_count = 148;
+    size_t smem_optin = 0;
+    bool profiling = false;
+    double profile[16] = {0};
+};
+Context& ctx();
+void require_init();
+
+// RAII device buffer (cudaMalloc / cudaFree); stream-ordered frees are not needed here.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return;
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+        if (e != cudaSuccess) { n = 0; throw CudaFail{e, "cudaMalloc", __FILE__, __LINE__}; }
+        p = (T*)q;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- model handle --------------------------------------------------------------------------------
+// Level-0 sorted point record of the grid: one 32-byte sector per point.
+struct __align__(32) GridPoint { double x, y, z; int32_t orig; int32_t pad; };
+struct __align__(32) ModelPointD { double x, y, z, pad; };
+
+constexpr int GRID_MAX_LEVELS = 12;
+
+struct GridView {               // passed by value to kernels
+    const GridPoint* pts;       // sorted by level-0 cell
+    const int32_t* cell_start;  // [ncell0 + 1]
+    const uint8_t* mask[GRID_MAX_LEVELS];   // mask[l], l >= 1: 8-bit child occupancy of level-l cells
+    int32_t dims[GRID_MAX_LEVELS][3];       // dims[l] of level l (level 0 = fine cells)
+    int32_t nlevels;            // root is level nlevels-1 (dims 1x1x1)
+    double origin[3];
+    double cell;                // level-0 edge
+    double inv_cell;
+};
+
+}  // namespace pcreg
+
+struct pcreg_model {
+    int64_t n = 0;              // points
+    int64_t n_pad = 0;          // padded to a multiple of the brute tile
+    double pivot[3] = {0, 0, 0};        // subtracted before the FP32 conversion and before the 17 sums
+    double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};
+    float  max_norm = 0.f;      // max |m32| over the model (FP32 error bound of the brute scan)
+    pcreg::DevBuf<float4> m4;               // shuffled scan order: (x,y,z relative to pivot, |.|^2)
+    pcreg::DevBuf<int32_t> perm;            // perm[scan position] = original index
+    pcreg::DevBuf<pcreg::ModelPointD> md;   // original order, FP64
+    // grid
+    bool has_grid = false;
+    pcreg::GridView grid{};
+    pcreg::DevBuf<pcreg::GridPoint> g_pts;
+    pcreg::DevBuf<int32_t> g_cell_start;
+    std::vector<pcreg::DevBuf<uint8_t>> g_masks;
+    int64_t g_occupied = 0;
+};
+
+namespace pcreg {
+
+// ---- internal launchers (implemented in the .cu files) ---------------------------------------------
+constexpr int BRUTE_TILE = 1024;            // model points per shared-memory tile (16 KB as float4)
+
+// Per-call scratch of the brute path (partial results of the model splits); grows on demand.
+struct NNScratch {
+    DevBuf<double> pd2;      // [nsplit][nq]
+    DevBuf<int32_t> pidx;    // [nsplit][nq]
+    DevBuf<float> pmin;      // [nsplit0][nq] sub-sample bound pass
+};
+
+// Nearest neighbour of quickTF(src_i, T_h) for every (h, i): exact FP64 decision.
+//   d_T   : [nhyp][16] row-major row-vector poses (device)
+//   prev  : optional [nhyp*ns] previous correspondences (warm start), may be nullptr
+//   out   : idx [nhyp*ns], d2 [nhyp*ns]
+void nn_brute_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz,
+                     int64_t ns, const double* d_T, int64_t nhyp, const int32_t* d_prev,
+                     int32_t* d_idx, double* d_d2, NNScratch& scratch, cudaStream_t st);
+void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz,
+                    int64_t ns, const double* d_T, int64_t nhyp, const int32_t* d_prev,
+                    int32_t* d_idx, double* d_d2, unsigned long long* d_visit_counters, cudaStream_t st);
+
+// Select / weight / 17 sums / Kabsch / compose, one block per hypothesis.
+struct IcpUpdateArgs {
+    const pcreg::ModelPointD* md;
+    double pivot[3];
+    const double* sx; const double* sy; const double* sz; const double* w_src;
+    int64_t ns;
+    double* T;                  // [nhyp][16] row-major, updated in place when `update`
+    const int32_t* idx; const double* d2;
+    unsigned long long* keys;   // [nhyp*ns] scratch (KNN mode)
+    int mode; double k_frac; double R_w; double thDist2; int reflection_fix;
+    int update;                 // 1: apply the pose update; 0: score only (final pass)
+    int32_t* frozen;            // [nhyp] status flags (1 = frozen)
+    double* rmse; int32_t* n_used;        // [nhyp] written every pass
+    double* rmse_hist; int hist_stride; int hist_col;   // optional
+};
+void icp_update_launch(const IcpUpdateArgs& a, int64_t nhyp, cudaStream_t st);
+void icp_argmin_launch(const double* d_rmse, int64_t nhyp, int64_t* d_best, cudaStream_t st);
+
+void grid_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st);
+// MATLAB column-major 4x4 <-> internal row-major 4x4, batched (a transpose either way)
+void transpose16_launch(const double* d_in, double* d_out, int64_t n, cudaStream_t st);
+
+}  // namespace pcreg

