@@ -113,7 +113,10 @@ def test_align_oracle_invariants():
     frame that differs by exactly that rotation (success threshold 0.5 at :221 is far away)."""
     for p in synth.make_neighbourhoods(4, 9):
         R = synth.rot_xyz([0.4, 1.0, -2.0])
-        for fn in (oracle.AlignPoints, lambda x: oracle.AlignPoints_KNN(x)[:2], lambda x: oracle.AlignPoints_weighted(x)[:2]):
+        # (AlignPoints_KNN is deliberately absent: its vote threshold is size(pts,1)/2 while only the K = 85 %
+        #  selected scores are counted (AlignPoints_KNN.m:37,45-46), so its signs depend on pca's sign
+        #  convention and are NOT rotation invariant -- a reference quirk the oracle and the kernel reproduce.)
+        for fn in (oracle.AlignPoints, lambda x: oracle.AlignPoints_weighted(x)[:2]):
             a1, c1 = fn(p)
             a2, c2 = fn(p @ R)
             assert oracle.check_alignment(R @ c2, c1) < 1e-6
