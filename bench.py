@@ -186,7 +186,7 @@ def gpu_workload(P, torch, w, rank, steps, warmup, dist=None, world=1, e2e_steps
     from pcreg_b200 import sharded, torch_ops
     dev = torch.device("cuda", torch.cuda.current_device())
     model_h, src, T0, w_src, T_gt = make_inputs(w, rank)
-    m = P.Model(model_h, grid=(w["nn"] == "grid"))
+    m = P.Model(model_h, grid=(w["nn"] == "grid"), cells_per_point=float(os.environ.get("PCREG_GRID_CPP", "0")))
     mode = dict(plain=P.ICP_PLAIN, knn=P.ICP_KNN, weighted=P.ICP_WEIGHTED)[w["mode"]]
     nn = P.NN_GRID if w["nn"] == "grid" else P.NN_BRUTE
     opts = P.icp_opts(mode=mode, iters=w["iters"], k_frac=0.85, R_w=3.5, nn=nn)

@@ -12,6 +12,8 @@
 //   winner        first-index arg-min of rmse (ransac.m:69-73 tie rule mirrored)
 #include <math.h>
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_icp_update(const __grid_constan
         nkept = block_sum_ll(nkept, redll);
         long long K = (long long)floor(a.k_frac * (double)nkept + 0.5);     // MATLAB round (AlignPoints_KNN.m:21)
         if (K > nkept) K = nkept;
-        block_radix_select(keys, ns, K, rsel, vK, all_eq);
+        block_radix_select(keys, ns, K, rsel, vK, all_eq, a.tie_order);
     }
 
     // ---- weights + the 17 sums ----
@@ -163,6 +165,79 @@ __global__ void __launch_bounds__(1024) k_icp_argmin(const double* __restrict__ 
     }
 }
 
+// ---- spatial sort of the source cloud (one block) ----------------------------------------------------
+// Threads of a warp then work on neighbouring queries under every pose (a rigid transform keeps
+// neighbours neighbours): the pyramid walks of a warp stay together and hit the same cache lines.
+// Results are un-permuted at the end; the stable tie rule of the trim keeps using ORIGINAL indices.
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void __launch_bounds__(1024) k_src_sort(const double* __restrict__ src, const double* __restrict__ w, int64_t ns,
+                                                   int npow2, unsigned long long* __restrict__ keys, double* __restrict__ out_src,
+                                                   double* __restrict__ out_w, int32_t* __restrict__ perm, int32_t* __restrict__ inv) {
+    __shared__ double red[6 * 32];
+    const int tid = threadIdx.x;
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = tid; i < ns; i += blockDim.x)
+        for (int a = 0; a < 3; ++a) { const double v = src[a * ns + i]; mn[a] = fmin(mn[a], v); mx[a] = fmax(mx[a], v); }
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) { mn[a] = fmin(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o)); mx[a] = fmax(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o)); }
+        if ((tid & 31) == 0) { red[a * 32 + (tid >> 5)] = mn[a]; red[(3 + a) * 32 + (tid >> 5)] = mx[a]; }
+    }
+    __syncthreads();
+    double ext = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) { lo = fmin(lo, red[a * 32 + wq]); hi = fmax(hi, red[(3 + a) * 32 + wq]); }
+        mn[a] = lo;
+        ext = fmax(ext, hi - lo);
+    }
+    const double scale = ext > 0.0 ? 1023.0 / ext : 0.0;
+    for (int i = tid; i < npow2; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < ns) {
+            const unsigned cx = (unsigned)((src[i] - mn[0]) * scale), cy = (unsigned)((src[ns + i] - mn[1]) * scale),
+                           cz = (unsigned)((src[2 * ns + i] - mn[2]) * scale);
+            const unsigned code = spread10(cx) | (spread10(cy) << 1) | (spread10(cz) << 2);
+            k = ((unsigned long long)code << 32) | (unsigned long long)(unsigned)i;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npow2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long x = keys[i], y = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int64_t r = tid; r < ns; r += blockDim.x) {
+        const int32_t o = (int32_t)(unsigned)(keys[r] & 0xffffffffull);
+        perm[r] = o;
+        inv[o] = (int32_t)r;
+        out_src[r] = src[o]; out_src[ns + r] = src[ns + o]; out_src[2 * ns + r] = src[2 * ns + o];
+        if (w) out_w[r] = w[o];
+    }
+}
+// out[h][orig] = in[h][inv[orig]]
+__global__ void k_unpermute_idx(const int32_t* __restrict__ in, const int32_t* __restrict__ inv, int64_t ns, int64_t nhyp,
+                                int32_t* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ns * nhyp) return;
+    const int64_t h = g / ns, o = g - h * ns;
+    out[g] = in[h * ns + inv[o]];
+}
+
 // MATLAB column-major 4x4 <-> internal row-major 4x4 (a transpose), batched
 __global__ void k_transpose16(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,6 +264,7 @@ void icp_argmin_launch(const double* d_rmse, int64_t nhyp, int64_t* d_best, cuda
 // host driver
 // ------------------------------------------------------------------------------------------------
 struct EventPair { cudaEvent_t a, b; int kind; };
+static bool debug_times() { static int v = -1; if (v < 0) { const char* e = getenv("PCREG_DEBUG_TIMES"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
 
 static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3, ld = ns*/, int64_t ns,
                     const double* d_w, const double* d_T0_cm, int64_t nhyp, const pcreg_icp_opts& o,
@@ -232,12 +308,26 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     auto ev_begin = [&](int kind) {
         if (!prof) return;
         EventPair e; e.kind = kind;
-        PCREG_CUDA(cudaEventCreate(&e.a)); PCREG_CUDA(cudaEventCreate(&e.b));
+        e.a = pooled_event(2 * evs.size()); e.b = pooled_event(2 * evs.size() + 1);
         PCREG_CUDA(cudaEventRecord(e.a, st));
         evs.push_back(e);
     };
     auto ev_end = [&]() { if (prof) PCREG_CUDA(cudaEventRecord(evs.back().b, st)); };
 
+    // spatial sort of the source (skipped for very large clouds: the single-block sort is sized for <= 2^17)
+    const bool sorted = ns >= 64 && ns <= (1 << 17);
+    DevBuf<double> src_sorted(sorted ? (size_t)ns * 3 : 0), w_sorted(sorted && d_w ? (size_t)ns : 0);
+    DevBuf<int32_t> sperm(sorted ? (size_t)ns : 0), sinv(sorted ? (size_t)ns : 0);
+    if (sorted) {
+        int npow2 = 1;
+        while (npow2 < ns) npow2 <<= 1;
+        DevBuf<unsigned long long> skeys((size_t)npow2);
+        k_src_sort<<<1, 1024, 0, st>>>(d_src, d_w, ns, npow2, skeys.p, src_sorted.p, d_w ? w_sorted.p : nullptr, sperm.p, sinv.p);
+        PCREG_LAUNCHED();
+        PCREG_CUDA(cudaStreamSynchronize(st));      // skeys is released here
+        d_src = src_sorted.p;
+        if (d_w) d_w = w_sorted.p;
+    }
     const double* sx = d_src; const double* sy = d_src + ns; const double* sz = d_src + 2 * ns;
     double nn_launches = 0, upd_launches = 0;
     for (int64_t h0 = 0; h0 < nhyp; h0 += hc) {
@@ -246,7 +336,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         bool have_prev = false;
         for (int it = 0; it <= o.iters; ++it) {
             const bool last = (it == o.iters);
-            int32_t* out_idx = (last && d_idx) ? d_idx + h0 * ns : cur;
+            int32_t* out_idx = (last && d_idx && !sorted) ? d_idx + h0 * ns : cur;
             ev_begin(0);
             if (o.nn == PCREG_NN_BRUTE)
                 nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p, scratch, st);
@@ -260,6 +350,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             for (int k = 0; k < 3; ++k) ua.pivot[k] = m->pivot[k];
             ua.sx = sx; ua.sy = sy; ua.sz = sz; ua.w_src = d_w; ua.ns = ns;
             ua.T = Twork.p + h0 * 16; ua.idx = out_idx; ua.d2 = d2.p; ua.keys = keys.p;
+            ua.tie_order = sorted ? sinv.p : nullptr;
             ua.mode = o.mode; ua.k_frac = o.k_frac; ua.R_w = o.R_w; ua.thDist2 = o.thDist2; ua.reflection_fix = o.reflection_fix;
             ua.update = last ? 0 : 1;
             ua.frozen = frozen.p + h0; ua.rmse = rm + h0; ua.n_used = nu + h0;
@@ -269,6 +360,10 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             icp_update_launch(ua, hn, st);
             ev_end();
             upd_launches += 1;
+            if (last && d_idx && sorted) {
+                k_unpermute_idx<<<(unsigned)((hn * ns + 255) / 256), 256, 0, st>>>(out_idx, sinv.p, ns, hn, d_idx + h0 * ns);
+                PCREG_LAUNCHED();
+            }
             std::swap(cur, prev);       // what was just written becomes the warm start
             have_prev = true;
         }
@@ -285,7 +380,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             float ms = 0.f;
             PCREG_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
             (e.kind == 0 ? nn_ms : upd_ms) += ms;
-            cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+            if (debug_times()) fprintf(stderr, "[pcreg] %s %.3f ms\n", e.kind == 0 ? "nn" : "update", ms);
         }
         unsigned long long hcnt[3] = {0, 0, 0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));

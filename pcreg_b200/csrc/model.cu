@@ -9,6 +9,8 @@
 #include <string.h>
 #include <math.h>
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <algorithm>
 
 #include "pcreg_internal.h"
@@ -29,6 +31,70 @@ void set_error(const char* fmt, ...) {
     memcpy(g_err_global, g_err, sizeof g_err);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- caching device allocator ----
+struct PoolBlock { void* p; size_t bytes; bool used; };
+static std::vector<PoolBlock> g_pool;
+static std::mutex g_pool_mu;
+static constexpr size_t POOL_KEEP_BYTES = (size_t)24 << 30;
+
+void* pool_alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_pool.size(); ++i) {
+            const PoolBlock& b = g_pool[i];
+            if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (best < 0 || b.bytes < g_pool[best].bytes)) best = i;
+        }
+        if (best >= 0) { g_pool[best].used = true; return g_pool[best].p; }
+    }
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim(0);                                   // give cached blocks back and retry once
+        e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) throw CudaFail{e, "cudaMalloc", __FILE__, __LINE__};
+    }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(PoolBlock{q, bytes, true});
+    return q;
+}
+void pool_free(void* p) {
+    if (!p) return;
+    size_t free_bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto& b : g_pool) {
+            if (b.p == p) b.used = false;
+            if (!b.used) free_bytes += b.bytes;
+        }
+    }
+    if (free_bytes > POOL_KEEP_BYTES) pool_trim(POOL_KEEP_BYTES / 2);
+}
+void pool_trim(size_t keep_bytes) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t free_bytes = 0;
+    for (auto& b : g_pool) if (!b.used) free_bytes += b.bytes;
+    for (size_t i = 0; i < g_pool.size() && free_bytes > keep_bytes;) {
+        if (!g_pool[i].used) {
+            cudaFree(g_pool[i].p);
+            free_bytes -= g_pool[i].bytes;
+            g_pool[i] = g_pool.back();
+            g_pool.pop_back();
+        } else ++i;
+    }
+}
+cudaEvent_t pooled_event(size_t i) {
+    Context& c = ctx();
+    while (c.events.size() <= i) {
+        cudaEvent_t e;
+        PCREG_CUDA(cudaEventCreate(&e));
+        c.events.push_back(e);
+    }
+    return c.events[i];
+}
 Context& ctx() { return g_ctx; }
 void require_init() {
     if (!g_ctx.initialised) throw ArgError{"pcreg_init has not been called (or failed): no CUDA device, and there is no CPU fallback"};
@@ -309,6 +375,12 @@ int pcreg_init(const int* devices, int ndev) {
 }
 
 int pcreg_shutdown(void) {
+    if (ctx().initialised) {
+        cudaDeviceSynchronize();
+        for (cudaEvent_t e : ctx().events) cudaEventDestroy(e);
+        ctx().events.clear();
+        pool_trim(0);
+    }
     ctx().initialised = false;
     return PCREG_OK;
 }

@@ -138,8 +138,11 @@ struct RadixSelShared {
     int run_eq;
 };
 
+// `order` (optional): order[r] = array position of the element whose tie-breaking rank is r (the array may
+// be stored in a permuted order, e.g. spatially sorted source points); nullptr = array order.
 __device__ __forceinline__ void block_radix_select(unsigned long long* __restrict__ keys, long long n, long long K,
-                                                   RadixSelShared& sh, unsigned long long& vK, bool& all_eq) {
+                                                   RadixSelShared& sh, unsigned long long& vK, bool& all_eq,
+                                                   const int32_t* __restrict__ order = nullptr) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     if (K <= 0) { vK = 0ull; all_eq = false; return; }        // nothing selected
     __syncthreads();
@@ -176,7 +179,8 @@ __device__ __forceinline__ void block_radix_select(unsigned long long* __restric
         __syncthreads();
         const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
         for (long long base = 0; base < n; base += nthr) {
-            const long long i = base + tid;
+            const long long r = base + tid;
+            const long long i = (r < n) ? (order ? (long long)order[r] : r) : n;
             const bool eq = i < n && keys[i] == vK;
             const unsigned bal = __ballot_sync(0xffffffffu, eq);
             if (lane == 0) sh.warp_cnt[warp] = __popc(bal);

@@ -55,11 +55,20 @@ struct Context {
     size_t smem_optin = 0;
     bool profiling = false;
     double profile[16] = {0};
+    std::vector<cudaEvent_t> events;     // reusable timing events (profiling mode)
 };
+cudaEvent_t pooled_event(size_t i);      // i-th reusable event, created on first use
 Context& ctx();
 void require_init();
 
-// RAII device buffer (cudaMalloc / cudaFree); stream-ordered frees are not needed here.
+// Caching device allocator: cudaMalloc / cudaFree cost milliseconds for the half-gigabyte scratch a
+// batch needs, so released blocks are kept and reused (best fit within 2x).  Blocks are only ever
+// released after the stream that used them has been synchronised.
+void* pool_alloc(size_t bytes);
+void pool_free(void* p);
+void pool_trim(size_t keep_bytes);
+
+// RAII device buffer on the caching allocator.
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -75,12 +84,9 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) return;
-        void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, count * sizeof(T));
-        if (e != cudaSuccess) { n = 0; throw CudaFail{e, "cudaMalloc", __FILE__, __LINE__}; }
-        p = (T*)q;
+        p = (T*)pool_alloc(count * sizeof(T));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) pool_free(p); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(T); }
 };
 
@@ -154,6 +160,7 @@ struct IcpUpdateArgs {
     double* T;                  // [nhyp][16] row-major, updated in place when `update`
     const int32_t* idx; const double* d2;
     unsigned long long* keys;   // [nhyp*ns] scratch (KNN mode)
+    const int32_t* tie_order;   // [ns] or null: tie_order[original index] = position in the (sorted) source arrays
     int mode; double k_frac; double R_w; double thDist2; int reflection_fix;
     int update;                 // 1: apply the pose update; 0: score only (final pass)
     int32_t* frozen;            // [nhyp] status flags (1 = frozen)

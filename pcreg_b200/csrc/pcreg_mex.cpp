@@ -1,0 +1,231 @@
+// pcreg_mex.cpp -- MEX gateway: MATLAB <-> the C ABI of include/pcreg.h.  Pure marshaling.
+//
+//   out = pcreg_mex('command', args...)
+//
+// Build (on a host with MATLAB):  mex -R2018a pcreg_mex.cpp -I../../include -L.. -lpcreg_b200
+// Conventions: inputs are borrowed read-only (mxGetData, never written); outputs are allocated with
+// mxCreate* (MATLAB owns them); "the reference returns []" -> a 0x0 double; CUDA / argument errors ->
+// mexErrMsgIdAndTxt (which long-jumps: it is only called after every C++ object of the frame is gone,
+// via the fail() pattern below).  The model handle travels as a uint64 scalar.  Indices are converted
+// to MATLAB's 1-based convention here.
+//
+// Commands (the matlab/*.m shims call these with the reference's own signatures):
+//   'init'[, device]                                   -> []
+//   'model_create', pts(Nx3 single|double)[, grid]     -> handle (uint64)
+//   'model_destroy', handle
+//   'nn_search', handle, q(Nx3)[, 'grid']              -> idx (Nx1 double, 1-based), d2 (Nx1)
+//   'align', kind, pts(Nx3)[, C1, C2 | K]              -> pts_aligned, coeff_unambig, c      (AlignPoints*.m)
+//   'estimate_transform', pts1, pts2                   -> T (4x4) or []                      (estimateTransform.m)
+//   'ransac', pts1, pts2, coef(struct), triplets(Hx3, 1-based)
+//                                                      -> T, inlierIdx, numSuccess, maxInliers, pct  (ransac.m)
+//   'icp', handle, src(Nx3), T0(4x4xH), opts(struct)[, w_src]
+//                                                      -> T(4x4xH), rmse(Hx1), n_used, status, best(1-based), idx(NxH)
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "mex.h"
+#include "../../include/pcreg.h"
+
+namespace {
+
+bool g_init = false;
+std::string g_fail;                // set instead of throwing; reported after the frame unwinds
+
+void at_exit() { pcreg_shutdown(); g_init = false; }
+
+bool ensure_init(int device) {
+    if (g_init) return true;
+    const int dev[1] = {device};
+    if (pcreg_init(dev, 1) != PCREG_OK) { g_fail = pcreg_last_error(); return false; }
+    mexLock();
+    mexAtExit(at_exit);
+    g_init = true;
+    return true;
+}
+
+bool is_pts(const mxArray* a) { return a && (mxIsDouble(a) || mxIsSingle(a)) && !mxIsComplex(a) && mxGetN(a) == 3; }
+mxArray* empty() { return mxCreateDoubleMatrix(0, 0, mxREAL); }
+double field_or(const mxArray* s, const char* name, double dflt) {
+    if (!s || !mxIsStruct(s)) return dflt;
+    const mxArray* f = mxGetField(s, 0, name);
+    return (f && !mxIsEmpty(f)) ? mxGetScalar(f) : dflt;
+}
+pcreg_model* handle_of(const mxArray* a) {
+    if (!a || mxGetClassID(a) != mxUINT64_CLASS || mxGetNumberOfElements(a) != 1) return nullptr;
+    return (pcreg_model*)(uintptr_t)(*(const uint64_t*)mxGetData(a));
+}
+
+// ---- commands: each returns false with g_fail set on error ----
+bool cmd_model_create(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 2 || !is_pts(prhs[1])) { g_fail = "model_create: pts must be N x 3 single or double"; return false; }
+    pcreg_model_opts o;
+    memset(&o, 0, sizeof o);
+    o.build_grid = (nrhs > 2) ? (mxGetScalar(prhs[2]) != 0) : 1;
+    pcreg_model* m = nullptr;
+    const int64_t n = (int64_t)mxGetM(prhs[1]);
+    if (pcreg_model_create(mxGetData(prhs[1]), mxIsDouble(prhs[1]), n, n, &o, &m) != PCREG_OK) { g_fail = pcreg_last_error(); return false; }
+    plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+    *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)m;
+    return true;
+}
+
+bool cmd_nn_search(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    pcreg_model* m = nrhs > 1 ? handle_of(prhs[1]) : nullptr;
+    if (!m || nrhs < 3 || !is_pts(prhs[2])) { g_fail = "nn_search: need (handle, q Nx3)"; return false; }
+    const int64_t nq = (int64_t)mxGetM(prhs[2]);
+    std::vector<int32_t> idx((size_t)nq);
+    plhs[0] = mxCreateDoubleMatrix((mwSize)nq, 1, mxREAL);
+    mxArray* d2 = mxCreateDoubleMatrix((mwSize)nq, 1, mxREAL);
+    const int kind = (nrhs > 3) ? PCREG_NN_GRID : PCREG_NN_BRUTE;
+    const int rc = pcreg_nn_search(m, mxGetData(prhs[2]), mxIsDouble(prhs[2]), nq, nq, kind, idx.data(), mxGetPr(d2));
+    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); mxDestroyArray(d2); return false; }
+    double* o = mxGetPr(plhs[0]);
+    for (int64_t i = 0; i < nq; ++i) o[i] = (double)idx[(size_t)i] + 1.0;
+    if (nlhs > 1) plhs[1] = d2; else mxDestroyArray(d2);
+    return true;
+}
+
+bool cmd_align(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 3 || !is_pts(prhs[2])) { g_fail = "align: need (kind, pts Nx3)"; return false; }
+    const int kind = (int)mxGetScalar(prhs[1]);
+    pcreg_align_opts o;
+    pcreg_align_opts_default(&o);
+    if (kind == PCREG_ALIGN_KNN_FRAC && nrhs >= 5) { o.C1 = mxGetScalar(prhs[3]) != 0; o.C2 = mxGetScalar(prhs[4]) != 0; }
+    if (kind == PCREG_ALIGN_KNN_ABS && nrhs >= 4) o.k_abs = (int64_t)mxGetScalar(prhs[3]);
+    const int64_t n = (int64_t)mxGetM(prhs[2]);
+    const int is_double = mxIsDouble(prhs[2]);
+    const int64_t offsets[2] = {0, n};
+    mxArray* out = mxCreateNumericMatrix((mwSize)n, 3, is_double ? mxDOUBLE_CLASS : mxSINGLE_CLASS, mxREAL);
+    mxArray* coeff = mxCreateDoubleMatrix(3, 3, mxREAL);
+    mxArray* c = mxCreateDoubleMatrix(1, 3, mxREAL);
+    int32_t status = 0;
+    const int rc = pcreg_align_points(kind, mxGetData(prhs[2]), is_double, n, offsets, 1, &o, mxGetData(out), mxGetPr(coeff), mxGetPr(c), &status);
+    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); mxDestroyArray(out); mxDestroyArray(coeff); mxDestroyArray(c); return false; }
+    if (status != 0) {                      // AlignPoints_c.m:16-18 / AlignPoints_KNN_c.m:53-56: [] , []
+        mxDestroyArray(out); mxDestroyArray(coeff);
+        out = empty(); coeff = empty();
+    }
+    plhs[0] = out;
+    if (nlhs > 1) plhs[1] = coeff; else mxDestroyArray(coeff);
+    if (nlhs > 2) plhs[2] = c; else mxDestroyArray(c);
+    return true;
+}
+
+bool cmd_estimate_transform(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 3 || !mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || mxGetN(prhs[1]) != 3 || mxGetN(prhs[2]) != 3 ||
+        mxGetM(prhs[1]) != mxGetM(prhs[2])) { g_fail = "estimate_transform: need two N x 3 double arrays"; return false; }
+    const int64_t n = (int64_t)mxGetM(prhs[1]);
+    const int64_t offsets[2] = {0, n};
+    mxArray* T = mxCreateDoubleMatrix(4, 4, mxREAL);
+    int32_t status = 0;
+    const int rc = pcreg_kabsch_batch(mxGetPr(prhs[1]), mxGetPr(prhs[2]), nullptr, n, offsets, 1, 0, mxGetPr(T), &status);
+    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); mxDestroyArray(T); return false; }
+    if (status != 0) { mxDestroyArray(T); T = empty(); }              // estimateTransform.m:11-14
+    plhs[0] = T;
+    return true;
+}
+
+bool cmd_ransac(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 5 || !mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || !mxIsStruct(prhs[3]) || !mxIsDouble(prhs[4]) ||
+        mxGetN(prhs[1]) != 3 || mxGetN(prhs[2]) != 3 || mxGetN(prhs[4]) != 3) { g_fail = "ransac: need (pts1, pts2, coef, triplets Hx3)"; return false; }
+    const int64_t P = (int64_t)mxGetM(prhs[1]), H = (int64_t)mxGetM(prhs[4]);
+    pcreg_ransac_opts o;
+    o.thDist = field_or(prhs[3], "thDist", 0.5);
+    o.thInlrRatio = field_or(prhs[3], "thInlrRatio", 0.1);
+    o.refine = field_or(prhs[3], "REFINE", 1.0) != 0;
+    o.reflection_fix = 0;
+    std::vector<int32_t> tri((size_t)H * 3), inl((size_t)P);
+    const double* t = mxGetPr(prhs[4]);
+    for (int64_t h = 0; h < H; ++h)
+        for (int k = 0; k < 3; ++k) tri[(size_t)h * 3 + k] = (int32_t)t[k * H + h] - 1;
+    double T16[16];
+    int64_t n_inl = 0, n_succ = 0, max_inl = 0, best = -1;
+    const int rc = pcreg_ransac_score(mxGetPr(prhs[1]), mxGetPr(prhs[2]), P, P, tri.data(), H, &o, T16, inl.data(), &n_inl, &n_succ,
+                                      &max_inl, &best, nullptr, nullptr, nullptr);
+    if (rc < 0) { g_fail = pcreg_last_error(); return false; }
+    if (rc == PCREG_DEGENERATE) {                                       // ransac.m:75-89
+        plhs[0] = empty();
+        if (nlhs > 1) plhs[1] = empty();
+        for (int k = 2; k < nlhs && k < 5; ++k) plhs[k] = mxCreateDoubleScalar(0.0);
+        return true;
+    }
+    plhs[0] = mxCreateDoubleMatrix(4, 4, mxREAL);
+    memcpy(mxGetPr(plhs[0]), T16, sizeof T16);
+    if (nlhs > 1) {
+        plhs[1] = mxCreateDoubleMatrix((mwSize)n_inl, 1, mxREAL);
+        for (int64_t i = 0; i < n_inl; ++i) mxGetPr(plhs[1])[i] = (double)inl[(size_t)i] + 1.0;
+    }
+    if (nlhs > 2) plhs[2] = mxCreateDoubleScalar((double)n_succ);
+    if (nlhs > 3) plhs[3] = mxCreateDoubleScalar((double)max_inl);
+    if (nlhs > 4) plhs[4] = mxCreateDoubleScalar(100.0 * (double)max_inl / (double)P);
+    return true;
+}
+
+bool cmd_icp(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    pcreg_model* m = nrhs > 1 ? handle_of(prhs[1]) : nullptr;
+    if (!m || nrhs < 5 || !is_pts(prhs[2]) || !mxIsDouble(prhs[3]) || mxGetNumberOfElements(prhs[3]) % 16 != 0) {
+        g_fail = "icp: need (handle, src Nx3, T0 4x4xH double, opts struct[, w_src])";
+        return false;
+    }
+    pcreg_icp_opts o;
+    pcreg_icp_opts_default(&o);
+    o.mode = (int)field_or(prhs[4], "mode", o.mode);
+    o.iters = (int)field_or(prhs[4], "iters", o.iters);
+    o.k_frac = field_or(prhs[4], "k_frac", o.k_frac);
+    o.R_w = field_or(prhs[4], "R_w", o.R_w);
+    o.thDist2 = field_or(prhs[4], "thDist2", o.thDist2);
+    o.nn = (int)field_or(prhs[4], "nn", o.nn);
+    o.reflection_fix = (int)field_or(prhs[4], "reflection_fix", 0);
+    const int64_t ns = (int64_t)mxGetM(prhs[2]);
+    const int64_t H = (int64_t)(mxGetNumberOfElements(prhs[3]) / 16);
+    const double* w = (nrhs > 5 && mxIsDouble(prhs[5]) && (int64_t)mxGetNumberOfElements(prhs[5]) == ns) ? mxGetPr(prhs[5]) : nullptr;
+    mxArray* T = mxCreateDoubleMatrix(16, (mwSize)H, mxREAL);            // reshaped to 4x4xH by the .m shim
+    mxArray* rmse = mxCreateDoubleMatrix((mwSize)H, 1, mxREAL);
+    mxArray* nu = mxCreateNumericMatrix((mwSize)H, 1, mxINT32_CLASS, mxREAL);
+    mxArray* st = mxCreateNumericMatrix((mwSize)H, 1, mxINT32_CLASS, mxREAL);
+    mxArray* idx = (nlhs > 5) ? mxCreateNumericMatrix((mwSize)ns, (mwSize)H, mxINT32_CLASS, mxREAL) : nullptr;
+    int64_t best = -1;
+    const int rc = pcreg_icp_batch(m, mxGetData(prhs[2]), mxIsDouble(prhs[2]), ns, ns, w, mxGetPr(prhs[3]), H, &o, mxGetPr(T), mxGetPr(rmse),
+                                   (int32_t*)mxGetData(nu), (int32_t*)mxGetData(st), idx ? (int32_t*)mxGetData(idx) : nullptr, nullptr, &best);
+    if (rc != PCREG_OK) {
+        g_fail = pcreg_last_error();
+        mxDestroyArray(T); mxDestroyArray(rmse); mxDestroyArray(nu); mxDestroyArray(st); if (idx) mxDestroyArray(idx);
+        return false;
+    }
+    if (idx) { int32_t* p = (int32_t*)mxGetData(idx); for (int64_t i = 0; i < ns * H; ++i) p[i] += 1; }
+    plhs[0] = T;
+    if (nlhs > 1) plhs[1] = rmse; else mxDestroyArray(rmse);
+    if (nlhs > 2) plhs[2] = nu; else mxDestroyArray(nu);
+    if (nlhs > 3) plhs[3] = st; else mxDestroyArray(st);
+    if (nlhs > 4) plhs[4] = mxCreateDoubleScalar((double)best + 1.0);
+    if (nlhs > 5) plhs[5] = idx;
+    return true;
+}
+
+}  // namespace
+
+extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    g_fail.clear();
+    bool ok = false;
+    {
+        char cmd[64] = "";
+        if (nrhs < 1 || !mxIsChar(prhs[0]) || mxGetString(prhs[0], cmd, sizeof cmd) != 0) {
+            g_fail = "pcreg_mex: first argument must be a command string";
+        } else if (!strcmp(cmd, "init")) {
+            ok = ensure_init(nrhs > 1 ? (int)mxGetScalar(prhs[1]) : 0);
+            if (ok && nlhs > 0) plhs[0] = empty();
+        } else if (!ensure_init(0)) {
+            ok = false;
+        } else if (!strcmp(cmd, "model_create")) ok = cmd_model_create(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "model_destroy")) { pcreg_model_destroy(nrhs > 1 ? handle_of(prhs[1]) : nullptr); ok = true; if (nlhs > 0) plhs[0] = empty(); }
+        else if (!strcmp(cmd, "nn_search")) ok = cmd_nn_search(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "align")) ok = cmd_align(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "estimate_transform")) ok = cmd_estimate_transform(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "ransac")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "icp")) ok = cmd_icp(nlhs, plhs, nrhs, prhs);
+        else g_fail = std::string("pcreg_mex: unknown command '") + cmd + "'";
+    }
+    // every C++ object of the frame above is destroyed; only now may MATLAB long-jump
+    if (!ok) mexErrMsgIdAndTxt("pcreg:error", "%s", g_fail.c_str());
+}
