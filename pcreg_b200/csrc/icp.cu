@@ -297,6 +297,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     DevBuf<int32_t> nused_tmp(d_n_used ? 0 : (size_t)nhyp);
     DevBuf<unsigned long long> counters(3);
     NNScratch scratch;
+    GridScratch gscratch;
     double* rm = d_rmse ? d_rmse : rmse_tmp.p;
     int32_t* nu = d_n_used ? d_n_used : nused_tmp.p;
 
@@ -342,7 +343,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
                 nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p, scratch, st);
             else
                 nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p,
-                               prof ? counters.p : nullptr, st);
+                               prof ? counters.p : nullptr, gscratch, st);
             ev_end();
             nn_launches += 1;
             IcpUpdateArgs ua{};
@@ -475,6 +476,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
     DevBuf<int32_t> d_idx((size_t)nq);
     DevBuf<unsigned long long> counters(3);
     NNScratch scratch;
+    GridScratch gscratch;
     PCREG_CUDA(cudaMemcpyAsync(d_q.p, hq.data(), d_q.bytes(), cudaMemcpyHostToDevice, st));
     PCREG_CUDA(cudaMemcpyAsync(d_T.p, I16, sizeof I16, cudaMemcpyHostToDevice, st));
     PCREG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
@@ -484,7 +486,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         nn_brute_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p, scratch, st);
     else
         nn_grid_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p,
-                       c.profiling ? counters.p : nullptr, st);
+                       c.profiling ? counters.p : nullptr, gscratch, st);
     if (c.profiling) PCREG_CUDA(cudaEventRecord(e1, st));
     PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
     if (d2) PCREG_CUDA(cudaMemcpyAsync(d2, d_d2.p, d_d2.bytes(), cudaMemcpyDeviceToHost, st));

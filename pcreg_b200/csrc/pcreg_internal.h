@@ -147,9 +147,15 @@ struct NNScratch {
 void nn_brute_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz,
                      int64_t ns, const double* d_T, int64_t nhyp, const int32_t* d_prev,
                      int32_t* d_idx, double* d_d2, NNScratch& scratch, cudaStream_t st);
+// Per-call scratch of the grid path: the work list handed from the direct kernel to the walk kernel.
+struct GridScratch {
+    DevBuf<int32_t> worklist;       // [nq]
+    DevBuf<unsigned int> count;     // [1]
+};
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz,
                     int64_t ns, const double* d_T, int64_t nhyp, const int32_t* d_prev,
-                    int32_t* d_idx, double* d_d2, unsigned long long* d_visit_counters, cudaStream_t st);
+                    int32_t* d_idx, double* d_d2, unsigned long long* d_visit_counters, GridScratch& scratch,
+                    cudaStream_t st);
 
 // Select / weight / 17 sums / Kabsch / compose, one block per hypothesis.
 struct IcpUpdateArgs {
