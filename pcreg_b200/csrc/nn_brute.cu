@@ -27,6 +27,7 @@
 //                blockIdx.y; partial (d2, idx) winners are merged by a small kernel.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 #include "pcreg_internal.h"
@@ -49,9 +50,9 @@ struct BruteArgs {
     const double* sx; const double* sy; const double* sz; int64_t ns;
     const double* T; int64_t nq;
     double px, py, pz; float max_norm;
-    int tile0;                  // first tile of the scanned range
-    int ntiles;                 // tiles in the scanned range
-    int tiles_per_split;
+    int64_t p_begin;            // scanned range of scan positions [p_begin, p_end)  (multiples of the group size)
+    int64_t p_end;
+    int64_t split_len;          // scan positions per blockIdx.y (multiple of the group size)
     const int32_t* prev;        // [nq] or null
     const float* bound_in;      // [nbound][nq] or null
     int nbound;
@@ -59,78 +60,101 @@ struct BruteArgs {
     double* pd2; int32_t* pidx; // exact output [gridDim.y][nq]
 };
 
-struct SlowState { float thr; float best32; double best64; int32_t bidx; };
+// FP32 error band of one query: 2E with E = coef * (|q32| + max|m32|)^2, from the scan coefficients
+// (ax,ay,az) = -2 * q32.  One function so that the prologue and the slow path agree bit for bit.
+__device__ __forceinline__ float brute_two_e(float ax, float ay, float az, float max_norm) {
+    const float qn = 0.5f * __fsqrt_ru(__fmaf_ru(ax, ax, __fmaf_ru(ay, ay, __fmul_ru(az, az))));
+    const float s = __fadd_ru(qn, max_norm);
+    return __fmul_ru(__fmul_ru(2.02f * BRUTE_ERR_COEF, s), s);
+}
 
-// Re-scan one group for one query; exact FP64 evaluation of everything inside the band.
-__device__ __noinline__ SlowState nn_slow(const float4* __restrict__ grp, int64_t jbase, float ax, float ay, float az,
-                                          float twoE, SlowState s, int64_t g, const BruteArgs& a) {
+// Re-scan one group for one query; exact FP64 evaluation of everything inside the band.  The exact
+// running winner (d2, original index) lives in the kernel's output arrays (global memory): the slow path is
+// rare, and keeping that state out of registers leaves the hot loop with 4 registers per query.
+// Returns the tightened threshold.
+__device__ __noinline__ float nn_slow(const float4* __restrict__ grp, int64_t jbase, float ax, float ay, float az,
+                                      float thr, int64_t g, int64_t o, const BruteArgs& a) {
     const int64_t h = g / a.ns, i = g - h * a.ns;
     double qx, qy, qz;
     quick_tf(a.T + h * 16, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
+    const float twoE = brute_two_e(ax, ay, az, a.max_norm);
+    double best64 = a.pd2[o];
+    int32_t bidx = a.pidx[o];
 #pragma unroll 1
     for (int j = 0; j < BRUTE_G; ++j) {
         const float4 m = grp[j];
         float d = fmaf(ax, m.x, m.w);
         d = fmaf(ay, m.y, d);
         d = fmaf(az, m.z, d);
-        if (d <= s.thr) {
+        if (d <= thr) {
             const int32_t orig = a.perm[jbase + j];
             if (orig >= 0) {
                 const ModelPointD p = a.md[orig];
                 const double d64 = dist2_exact(p.x, p.y, p.z, qx, qy, qz);
-                if (d64 < s.best64 || (d64 == s.best64 && orig < s.bidx)) { s.best64 = d64; s.bidx = orig; }
-                if (d < s.best32) { s.best32 = d; s.thr = __fadd_ru(d, twoE); }
+                if (d64 < best64 || (d64 == best64 && (bidx < 0 || orig < bidx))) { best64 = d64; bidx = orig; }
+                const float cand = __fadd_ru(d, twoE);
+                if (cand < thr) thr = cand;
             }
         }
     }
-    return s;
+    a.pd2[o] = best64;
+    a.pidx[o] = bidx;
+    return thr;
 }
+
+constexpr int BRUTE_STAGES = 4;             // shared-memory ring of model tiles
+constexpr int BRUTE_PREFETCH = 2;           // tiles in flight ahead of the consumer (ring slack = STAGES - PREFETCH - 1 tiles)
+constexpr int BRUTE_WARPS = BRUTE_THREADS / 32;
+constexpr size_t BRUTE_SMEM = (size_t)BRUTE_STAGES * BRUTE_TILE * sizeof(float4) + 2 * BRUTE_STAGES * sizeof(uint64_t);
 
 template <int Q, bool PURE_MIN>
 __global__ void __launch_bounds__(BRUTE_THREADS, 2) k_nn_brute(const __grid_constant__ BruteArgs a) {
-    __shared__ __align__(128) float4 tile[2][BRUTE_TILE];
-    __shared__ __align__(8) uint64_t full[2];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);                                        // [STAGES][TILE]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)BRUTE_STAGES * BRUTE_TILE * sizeof(float4));
+    uint64_t* empty = full + BRUTE_STAGES;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int64_t qbase = (int64_t)blockIdx.x * (BRUTE_THREADS * Q);
-    const int t_begin = a.tile0 + blockIdx.y * a.tiles_per_split;
-    int t_end = t_begin + a.tiles_per_split;
-    if (t_end > a.tile0 + a.ntiles) t_end = a.tile0 + a.ntiles;
-    const int nt = t_end - t_begin;
+    const int64_t r_begin = a.p_begin + (int64_t)blockIdx.y * a.split_len;
+    const int64_t r_end = min(a.p_end, r_begin + a.split_len);
+    const int nt = r_end > r_begin ? (int)((r_end - r_begin + BRUTE_TILE - 1) / BRUTE_TILE) : 0;
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int s = 0; s < BRUTE_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BRUTE_WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
-    constexpr uint32_t TILE_BYTES = BRUTE_TILE * sizeof(float4);
-    if (tid == 0 && nt > 0) {
-        mbar_expect_tx(&full[0], TILE_BYTES);
-        bulk_g2s(&tile[0][0], a.m4 + (int64_t)t_begin * BRUTE_TILE, TILE_BYTES, &full[0]);
-    }
+    // producer (thread 0): tile t -> stage t % STAGES, after every warp released the stage's previous tile
+    auto issue_tile = [&](int t) {
+        const int st = t % BRUTE_STAGES;
+        if (t >= BRUTE_STAGES) mbar_wait(&empty[st], (uint32_t)(((t / BRUTE_STAGES) - 1) & 1));
+        const int64_t start = r_begin + (int64_t)t * BRUTE_TILE;
+        const uint32_t bytes = (uint32_t)(min((int64_t)BRUTE_TILE, r_end - start) * (int64_t)sizeof(float4));
+        mbar_expect_tx(&full[st], bytes);
+        bulk_g2s(tiles + (size_t)st * BRUTE_TILE, a.m4 + start, bytes, &full[st]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < BRUTE_PREFETCH && t < nt; ++t) issue_tile(t);
 
-    // ---- per-thread query state ----
-    float ax[Q], ay[Q], az[Q], thr[Q], best32[Q], twoE[Q];
-    double best64[Q];
-    int32_t bidx[Q];
+    // ---- per-thread query state: 4 registers per query in the hot loop ----
+    float ax[Q], ay[Q], az[Q], thr[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
         const int64_t g = qbase + (int64_t)k * BRUTE_THREADS + tid;
         ax[k] = ay[k] = az[k] = 0.f;
-        thr[k] = -FLT_MAX; best32[k] = FLT_MAX; twoE[k] = 0.f;
-        best64[k] = INFINITY; bidx[k] = -1;
+        thr[k] = PURE_MIN ? FLT_MAX : -FLT_MAX;           // PURE_MIN: thr is the running minimum itself
         if (g < a.nq) {
             const int64_t h = g / a.ns, i = g - h * a.ns;
             double qx, qy, qz;
             quick_tf(a.T + h * 16, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
             const float fx = __double2float_rn(qx - a.px), fy = __double2float_rn(qy - a.py), fz = __double2float_rn(qz - a.pz);
             ax[k] = -2.f * fx; ay[k] = -2.f * fy; az[k] = -2.f * fz;
-            const float qn = __fsqrt_ru(__fmaf_ru(fx, fx, __fmaf_ru(fy, fy, __fmul_ru(fz, fz))));
-            const float s = __fadd_ru(qn, a.max_norm);
-            twoE[k] = __fmul_ru(__fmul_ru(2.02f * BRUTE_ERR_COEF, s), s);
-            float bound = FLT_MAX;
             if (!PURE_MIN) {
+                const int64_t o = (int64_t)blockIdx.y * a.nq + g;
+                a.pd2[o] = INFINITY;
+                a.pidx[o] = -1;
+                float bound = FLT_MAX;
                 if (a.prev) {
                     const int32_t p = a.prev[g];
                     if (p >= 0) {
@@ -145,24 +169,22 @@ __global__ void __launch_bounds__(BRUTE_THREADS, 2) k_nn_brute(const __grid_cons
                 } else if (a.bound_in) {
                     for (int b = 0; b < a.nbound; ++b) bound = fminf(bound, a.bound_in[(int64_t)b * a.nq + g]);
                 }
-                best32[k] = bound;
-                thr[k] = (bound < FLT_MAX) ? __fadd_ru(bound, twoE[k]) : FLT_MAX;
+                thr[k] = (bound < FLT_MAX) ? __fadd_ru(bound, brute_two_e(ax[k], ay[k], az[k], a.max_norm)) : FLT_MAX;
             }
         }
     }
 
-    // ---- stream the model tiles ----
+    // ---- stream the model tiles through the ring ----
 #pragma unroll 1
     for (int it = 0; it < nt; ++it) {
-        const int cur = it & 1;
-        if (tid == 0 && it + 1 < nt) {
-            mbar_expect_tx(&full[cur ^ 1], TILE_BYTES);
-            bulk_g2s(&tile[cur ^ 1][0], a.m4 + (int64_t)(t_begin + it + 1) * BRUTE_TILE, TILE_BYTES, &full[cur ^ 1]);
-        }
-        mbar_wait(&full[cur], (uint32_t)((it >> 1) & 1));
-        const float4* __restrict__ tp = &tile[cur][0];
+        const int st = it % BRUTE_STAGES;
+        if (tid == 0 && it + BRUTE_PREFETCH < nt) issue_tile(it + BRUTE_PREFETCH);
+        mbar_wait(&full[st], (uint32_t)((it / BRUTE_STAGES) & 1));
+        const float4* __restrict__ tp = tiles + (size_t)st * BRUTE_TILE;
+        const int64_t tstart = r_begin + (int64_t)it * BRUTE_TILE;
+        const int tlen = (int)min((int64_t)BRUTE_TILE, r_end - tstart);
 #pragma unroll 1
-        for (int g0 = 0; g0 < BRUTE_TILE; g0 += BRUTE_G) {
+        for (int g0 = 0; g0 < tlen; g0 += BRUTE_G) {
             float gm[Q];
 #pragma unroll
             for (int jj = 0; jj < BRUTE_G; jj += 2) {
@@ -175,7 +197,7 @@ __global__ void __launch_bounds__(BRUTE_THREADS, 2) k_nn_brute(const __grid_cons
                     d1 = fmaf(ay[k], m1.y, d1);
                     d0 = fmaf(az[k], m0.z, d0);
                     d1 = fmaf(az[k], m1.z, d1);
-                    if (PURE_MIN)      best32[k] = fmin3(best32[k], d0, d1);
+                    if (PURE_MIN)      thr[k] = fmin3(thr[k], d0, d1);
                     else if (jj == 0)  gm[k] = fminf(d0, d1);
                     else               gm[k] = fmin3(gm[k], d0, d1);
                 }
@@ -185,29 +207,26 @@ __global__ void __launch_bounds__(BRUTE_THREADS, 2) k_nn_brute(const __grid_cons
 #pragma unroll
                 for (int k = 0; k < Q; ++k) hit |= (gm[k] <= thr[k]);
                 if (hit) {
-                    const int64_t jbase = (int64_t)(t_begin + it) * BRUTE_TILE + g0;
+                    const int64_t jbase = tstart + g0;
 #pragma unroll
                     for (int k = 0; k < Q; ++k) {
                         if (gm[k] <= thr[k]) {
-                            SlowState s{thr[k], best32[k], best64[k], bidx[k]};
-                            s = nn_slow(tp + g0, jbase, ax[k], ay[k], az[k], twoE[k], s,
-                                        qbase + (int64_t)k * BRUTE_THREADS + tid, a);
-                            thr[k] = s.thr; best32[k] = s.best32; best64[k] = s.best64; bidx[k] = s.bidx;
+                            const int64_t g = qbase + (int64_t)k * BRUTE_THREADS + tid;
+                            thr[k] = nn_slow(tp + g0, jbase, ax[k], ay[k], az[k], thr[k], g, (int64_t)blockIdx.y * a.nq + g, a);
                         }
                     }
                 }
             }
         }
-        __syncthreads();        // everyone is done with tile[cur] before it is refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);     // this warp is done with the stage
     }
 
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
         const int64_t g = qbase + (int64_t)k * BRUTE_THREADS + tid;
         if (g < a.nq) {
-            const int64_t o = (int64_t)blockIdx.y * a.nq + g;
-            if (PURE_MIN) a.pmin[o] = best32[k];
-            else { a.pd2[o] = best64[k]; a.pidx[o] = bidx[k]; }
+            if (PURE_MIN) a.pmin[(int64_t)blockIdx.y * a.nq + g] = thr[k];
         }
     }
 }
@@ -232,33 +251,40 @@ template <int Q>
 static void brute_run(const pcreg_model* m, BruteArgs a, const int32_t* d_prev, int32_t* d_idx, double* d_d2,
                       NNScratch& sc, cudaStream_t st) {
     const int64_t nq = a.nq;
-    const int ntiles_all = (int)(m->n_pad / BRUTE_TILE);
     const int64_t qblocks = (nq + BRUTE_THREADS * Q - 1) / (BRUTE_THREADS * Q);
-    const int target_blocks = ctx().sm_count * 4;
-    auto plan_split = [&](int ntiles, int& nsplit, int& tps) {
-        int want = (int)std::max<int64_t>(1, (target_blocks + qblocks - 1) / qblocks);
-        want = std::min(want, std::max(1, ntiles / 2));
-        tps = (ntiles + want - 1) / want;
-        nsplit = (ntiles + tps - 1) / tps;
+    const int slots = ctx().sm_count * 2;                  // co-resident blocks (2 per SM)
+    static bool attr_set = false;
+    if (!attr_set) {
+        PCREG_CUDA(cudaFuncSetAttribute(k_nn_brute<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRUTE_SMEM));
+        PCREG_CUDA(cudaFuncSetAttribute(k_nn_brute<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRUTE_SMEM));
+        attr_set = true;
+    }
+    // Few query blocks: split the MODEL range so that all blocks fit in ONE wave with equal work
+    // (split boundaries are multiples of the group size, not of the tile).  Many query blocks: no split.
+    auto plan_split = [&](int64_t npts, int& nsplit, int64_t& len) {
+        int64_t want = qblocks >= slots ? 1 : slots / qblocks;
+        want = std::max<int64_t>(1, std::min<int64_t>(want, npts / (4 * BRUTE_G)));
+        len = ((npts + want - 1) / want + BRUTE_G - 1) / BRUTE_G * BRUTE_G;
+        nsplit = (int)((npts + len - 1) / len);
     };
     a.prev = d_prev;
     a.bound_in = nullptr; a.nbound = 0;
     if (!d_prev) {
         // bound pass: pure minimum of d' over the first 1/8 of the (randomly ordered) scan array
-        const int nsub = std::max(1, ntiles_all / 8);
-        int ns0, tps0;
-        plan_split(nsub, ns0, tps0);
+        const int64_t nsub = std::max<int64_t>(BRUTE_G, (m->n_pad / 8) / BRUTE_G * BRUTE_G);
+        int ns0; int64_t len0;
+        plan_split(nsub, ns0, len0);
         if (sc.pmin.n < (size_t)ns0 * nq) sc.pmin.alloc((size_t)ns0 * nq);
         BruteArgs b = a;
-        b.tile0 = 0; b.ntiles = nsub; b.tiles_per_split = tps0; b.pmin = sc.pmin.p;
+        b.p_begin = 0; b.p_end = nsub; b.split_len = len0; b.pmin = sc.pmin.p;
         dim3 grid((unsigned)qblocks, (unsigned)ns0);
-        k_nn_brute<Q, true><<<grid, BRUTE_THREADS, 0, st>>>(b);
+        k_nn_brute<Q, true><<<grid, BRUTE_THREADS, BRUTE_SMEM, st>>>(b);
         PCREG_LAUNCHED();
         a.bound_in = sc.pmin.p; a.nbound = ns0;
     }
-    int nsplit, tps;
-    plan_split(ntiles_all, nsplit, tps);
-    a.tile0 = 0; a.ntiles = ntiles_all; a.tiles_per_split = tps;
+    int nsplit; int64_t len;
+    plan_split(m->n_pad, nsplit, len);
+    a.p_begin = 0; a.p_end = m->n_pad; a.split_len = len;
     if (nsplit == 1) {
         a.pd2 = d_d2; a.pidx = d_idx;
         if (!d_d2) { if (sc.pd2.n < (size_t)nq) sc.pd2.alloc((size_t)nq); a.pd2 = sc.pd2.p; }
@@ -268,7 +294,7 @@ static void brute_run(const pcreg_model* m, BruteArgs a, const int32_t* d_prev, 
         a.pd2 = sc.pd2.p; a.pidx = sc.pidx.p;
     }
     dim3 grid((unsigned)qblocks, (unsigned)nsplit);
-    k_nn_brute<Q, false><<<grid, BRUTE_THREADS, 0, st>>>(a);
+    k_nn_brute<Q, false><<<grid, BRUTE_THREADS, BRUTE_SMEM, st>>>(a);
     PCREG_LAUNCHED();
     if (nsplit > 1) {
         k_nn_merge<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(sc.pd2.p, sc.pidx.p, nsplit, nq, d_idx, d_d2);
@@ -285,8 +311,10 @@ void nn_brute_launch(const pcreg_model* m, const double* d_sx, const double* d_s
     a.px = m->pivot[0]; a.py = m->pivot[1]; a.pz = m->pivot[2]; a.max_norm = m->max_norm;
     PCREG_REQUIRE(a.nq > 0, "nn_brute: no queries");
     PCREG_REQUIRE((a.nq + BRUTE_THREADS * 4 - 1) / (BRUTE_THREADS * 4) < 2147483647LL, "nn_brute: too many queries in one launch");
-    // few queries: fewer per thread so that more threads share the work; many: 8 per thread
-    if (a.nq >= (int64_t)ctx().sm_count * BRUTE_THREADS * 8) brute_run<8>(m, a, d_prev, d_idx, d_d2, sc, st);
+    static int force_q = -1;
+    if (force_q < 0) { const char* e = getenv("PCREG_BRUTE_Q"); force_q = e ? atoi(e) : 0; }
+    const bool wide = force_q ? (force_q == 8) : true;    // 8 queries per thread measured faster at every size (profiles/)
+    if (wide) brute_run<8>(m, a, d_prev, d_idx, d_d2, sc, st);
     else                                                    brute_run<4>(m, a, d_prev, d_idx, d_d2, sc, st);
 }
 
