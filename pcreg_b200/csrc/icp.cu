@@ -19,6 +19,7 @@
 
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
+#include "pcreg_select.cuh"
 #include "pcreg_math.cuh"
 
 namespace pcreg {
@@ -26,11 +27,12 @@ namespace pcreg {
 constexpr int UPD_THREADS = 512;
 
 // One block per hypothesis.
-__global__ void __launch_bounds__(UPD_THREADS) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
+__global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
     __shared__ double Ts[16];
     __shared__ double red[KABSCH_NSUMS * 32];
     __shared__ long long redll[32];
-    __shared__ RadixSelShared rsel;
+    __shared__ HistSelShared hsel;
+    __shared__ unsigned long long red_u64[64];
 
     const int64_t h = blockIdx.x;
     const int tid = threadIdx.x;
@@ -46,16 +48,35 @@ __global__ void __launch_bounds__(UPD_THREADS) k_icp_update(const __grid_constan
     if (a.mode == PCREG_ICP_KNN) {
         unsigned long long* __restrict__ keys = a.keys + h * ns;
         long long nkept = 0;
+        unsigned long long kmin = ~0ull, kmax = 0ull;
         for (int64_t i = tid; i < ns; i += UPD_THREADS) {
             const double d = d2[i];
             const bool keep = idx[i] >= 0 && (!reject || d < a.thDist2);
-            keys[i] = keep ? dbits(__dsqrt_rn(d)) : KEY_NOSEL;
-            nkept += keep ? 1 : 0;
+            const unsigned long long key = keep ? dbits(__dsqrt_rn(d)) : KEY_NOSEL;
+            keys[i] = key;
+            if (keep) { ++nkept; kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
         }
         nkept = block_sum_ll(nkept, redll);
+        {   // block min / max of the kept keys
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long a0 = __shfl_xor_sync(0xffffffffu, kmin, o), a1 = __shfl_xor_sync(0xffffffffu, kmax, o);
+                kmin = a0 < kmin ? a0 : kmin;
+                kmax = a1 > kmax ? a1 : kmax;
+            }
+            if (lane == 0) { red_u64[warp] = kmin; red_u64[32 + warp] = kmax; }
+            __syncthreads();
+            kmin = ~0ull; kmax = 0ull;
+            for (int w = 0; w < UPD_THREADS / 32; ++w) {
+                kmin = red_u64[w] < kmin ? red_u64[w] : kmin;
+                kmax = red_u64[32 + w] > kmax ? red_u64[32 + w] : kmax;
+            }
+            __syncthreads();
+        }
         long long K = (long long)floor(a.k_frac * (double)nkept + 0.5);     // MATLAB round (AlignPoints_KNN.m:21)
         if (K > nkept) K = nkept;
-        block_radix_select(keys, ns, K, rsel, vK, all_eq, a.tie_order);
+        block_hist_select(keys, ns, K, kmin, kmax, hsel, vK, all_eq, a.tie_order);
     }
 
     // ---- weights + the 17 sums ----

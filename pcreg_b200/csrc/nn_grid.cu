@@ -74,8 +74,8 @@ struct Query {
 
 __device__ __forceinline__ void setup_query(const GridArgs& a, int64_t gq, Query& Q) {
     const GridView& G = a.g;
-    const int64_t h = gq / a.ns, i = gq - h * a.ns;
-    quick_tf(a.T + h * 16, a.sx[i], a.sy[i], a.sz[i], Q.qx, Q.qy, Q.qz);
+    const unsigned h = (unsigned)gq / (unsigned)a.ns, i = (unsigned)gq - h * (unsigned)a.ns;      // nq < 2^31 (launcher)
+    quick_tf(a.T + (size_t)h * 16, a.sx[i], a.sy[i], a.sz[i], Q.qx, Q.qy, Q.qz);
     Q.fx = __double2float_rn((Q.qx - G.origin[0]) * G.inv_cell);
     Q.fy = __double2float_rn((Q.qy - G.origin[1]) * G.inv_cell);
     Q.fz = __double2float_rn((Q.qz - G.origin[2]) * G.inv_cell);
