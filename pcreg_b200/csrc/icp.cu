@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_cons
         a.rmse[h] = rmse;
         a.n_used[h] = (int32_t)n_used;
         if (a.rmse_hist) a.rmse_hist[h * a.hist_stride + a.hist_col] = rmse;
+        float moved = 0.f;
         if (a.update && !a.frozen[h]) {
             if (n_used < 3 || !(sw > 0.0)) {
                 a.frozen[h] = 1;
@@ -143,8 +144,49 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_cons
                 for (int k = 0; k < 16; ++k) Tc[k] = Ts[k];
                 mul4(Tc, dT, Tn);
                 for (int k = 0; k < 16; ++k) a.T[h * 16 + k] = Tn[k];
+                if (a.delta) {
+                    // upper bound of how far this update moves any source point:
+                    // q' - q = (x - c)(R' - R) + [c (R' - R) + (t' - t)],  |x - c| <= r_max
+                    double fro = 0.0, v[3];
+                    for (int c = 0; c < 3; ++c) {
+                        v[c] = Tn[12 + c] - Tc[12 + c];
+                        for (int r = 0; r < 3; ++r) {
+                            const double dr = Tn[r * 4 + c] - Tc[r * 4 + c];
+                            fro += dr * dr;
+                            v[c] += a.src_stats[r] * dr;
+                        }
+                    }
+                    const double dl = sqrt(fro) * a.src_stats[3] + sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                    moved = __double2float_ru(dl * (1.0 + 1e-9)) + 1e-30f;
+                }
             }
         }
+        if (a.delta) a.delta[h] = moved;
+    }
+}
+
+// centroid and radius of the source cloud (for the per-update motion bound): one block
+__global__ void __launch_bounds__(1024) k_src_stats(const double* __restrict__ src, int64_t ns, double* __restrict__ stats /*[4]*/) {
+    __shared__ double red[3 * 32];
+    __shared__ double cen[3];
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < ns; i += blockDim.x) { s[0] += src[i]; s[1] += src[ns + i]; s[2] += src[2 * ns + i]; }
+    block_sum<3>(s, red);
+    if (threadIdx.x == 0) for (int k = 0; k < 3; ++k) cen[k] = s[k] / (double)ns;
+    __syncthreads();
+    double r2 = 0.0;
+    for (int64_t i = threadIdx.x; i < ns; i += blockDim.x) {
+        const double dx = src[i] - cen[0], dy = src[ns + i] - cen[1], dz = src[2 * ns + i] - cen[2];
+        r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+    }
+    for (int o = 16; o > 0; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        stats[0] = cen[0]; stats[1] = cen[1]; stats[2] = cen[2];
+        stats[3] = sqrt(m) * (1.0 + 1e-12);
     }
 }
 
@@ -316,9 +358,17 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     DevBuf<int32_t> frozen((size_t)nhyp);
     DevBuf<double> rmse_tmp(d_rmse ? 0 : (size_t)nhyp);
     DevBuf<int32_t> nused_tmp(d_n_used ? 0 : (size_t)nhyp);
-    DevBuf<unsigned long long> counters(3);
+    DevBuf<unsigned long long> counters(4);
     NNScratch scratch;
     GridScratch gscratch;
+    // temporal coherence (grid NN): per-query lower bound of the runner-up distance, per-hypothesis motion bound
+    // EXPERIMENTAL, off by default (PCREG_COHERENCE=1): on C3 only ~20-30 % of the steady-state queries certify
+    // (the runner-up is typically 0.02 mm away, the pose drifts 0.005-0.015 mm per iteration) and the larger
+    // exhaustive radius costs more than the skipped searches save (profiles/r01_notes.md).
+    static const bool coherence_on = [] { const char* e = getenv("PCREG_COHERENCE"); return e && e[0] == '1'; }();
+    const bool coherent = (o.nn == PCREG_NN_GRID) && coherence_on;
+    DevBuf<float> lb2(coherent ? (size_t)hc * ns : 0), delta(coherent ? (size_t)nhyp : 0);
+    DevBuf<double> src_stats(4);
     double* rm = d_rmse ? d_rmse : rmse_tmp.p;
     int32_t* nu = d_n_used ? d_n_used : nused_tmp.p;
 
@@ -351,11 +401,15 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         if (d_w) d_w = w_sorted.p;
     }
     const double* sx = d_src; const double* sy = d_src + ns; const double* sz = d_src + 2 * ns;
+    k_src_stats<<<1, 1024, 0, st>>>(d_src, ns, src_stats.p);
+    PCREG_LAUNCHED();
+    if (coherent) PCREG_CUDA(cudaMemsetAsync(delta.p, 0, delta.bytes(), st));
     double nn_launches = 0, upd_launches = 0;
     for (int64_t h0 = 0; h0 < nhyp; h0 += hc) {
         const int64_t hn = std::min(hc, nhyp - h0);
         int32_t* cur = idxA.p; int32_t* prev = idxB.p;
         bool have_prev = false;
+        if (coherent) PCREG_CUDA(cudaMemsetAsync(lb2.p, 0, (size_t)hn * ns * sizeof(float), st));
         for (int it = 0; it <= o.iters; ++it) {
             const bool last = (it == o.iters);
             int32_t* out_idx = (last && d_idx && !sorted) ? d_idx + h0 * ns : cur;
@@ -364,7 +418,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
                 nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p, scratch, st);
             else
                 nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p,
-                               prof ? counters.p : nullptr, gscratch, st);
+                               prof ? counters.p : nullptr, gscratch, coherent ? lb2.p : nullptr, coherent ? delta.p + h0 : nullptr, st);
             ev_end();
             nn_launches += 1;
             IcpUpdateArgs ua{};
@@ -373,6 +427,8 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             ua.sx = sx; ua.sy = sy; ua.sz = sz; ua.w_src = d_w; ua.ns = ns;
             ua.T = Twork.p + h0 * 16; ua.idx = out_idx; ua.d2 = d2.p; ua.keys = keys.p;
             ua.tie_order = sorted ? sinv.p : nullptr;
+            ua.delta = coherent ? delta.p + h0 : nullptr;
+            ua.src_stats = src_stats.p;
             ua.mode = o.mode; ua.k_frac = o.k_frac; ua.R_w = o.R_w; ua.thDist2 = o.thDist2; ua.reflection_fix = o.reflection_fix;
             ua.update = last ? 0 : 1;
             ua.frozen = frozen.p + h0; ua.rmse = rm + h0; ua.n_used = nu + h0;
@@ -404,8 +460,9 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             (e.kind == 0 ? nn_ms : upd_ms) += ms;
             if (debug_times()) fprintf(stderr, "[pcreg] %s %.3f ms\n", e.kind == 0 ? "nn" : "update", ms);
         }
-        unsigned long long hcnt[3] = {0, 0, 0};
+        unsigned long long hcnt[4] = {0, 0, 0, 0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
+        c.profile[10] = (double)hcnt[3];
         const double nq = (double)nhyp * (double)ns * (double)(o.iters + 1);
         c.profile[0] = nn_launches; c.profile[1] = nn_ms; c.profile[2] = nq;
         c.profile[3] = (o.nn == PCREG_NN_BRUTE) ? nq * (double)m->n : 0.0;
@@ -495,7 +552,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
     const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     DevBuf<double> d_q((size_t)nq * 3), d_T(16), d_d2((size_t)nq);
     DevBuf<int32_t> d_idx((size_t)nq);
-    DevBuf<unsigned long long> counters(3);
+    DevBuf<unsigned long long> counters(4);
     NNScratch scratch;
     GridScratch gscratch;
     PCREG_CUDA(cudaMemcpyAsync(d_q.p, hq.data(), d_q.bytes(), cudaMemcpyHostToDevice, st));
@@ -507,7 +564,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         nn_brute_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p, scratch, st);
     else
         nn_grid_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p,
-                       c.profiling ? counters.p : nullptr, gscratch, st);
+                       c.profiling ? counters.p : nullptr, gscratch, nullptr, nullptr, st);
     if (c.profiling) PCREG_CUDA(cudaEventRecord(e1, st));
     PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
     if (d2) PCREG_CUDA(cudaMemcpyAsync(d2, d_d2.p, d_d2.bytes(), cudaMemcpyDeviceToHost, st));
@@ -516,7 +573,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         float ms = 0.f;
         PCREG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         cudaEventDestroy(e0); cudaEventDestroy(e1);
-        unsigned long long hcnt[3] = {0, 0, 0};
+        unsigned long long hcnt[4] = {0, 0, 0, 0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
         c.profile[0] = 1; c.profile[1] = ms; c.profile[2] = (double)nq;
         c.profile[3] = nn_kind == PCREG_NN_BRUTE ? (double)nq * (double)m->n : 0.0;

@@ -32,6 +32,10 @@ struct GridArgs {
     const double* T; int64_t nq;
     const int32_t* prev;
     int32_t* idx; double* d2;
+    float* lb2;                     // [nq] in/out or null: lower bound of the distance from the query to every model point
+                                    //      OTHER than its correspondence (temporal-coherence certificate, see below)
+    const float* delta;             // [nhyp] or null: upper bound of how far the last pose update moved any source point
+    float gap_cells;                // the row scan is exhaustive within (best distance + gap), in cell units
     int32_t* worklist;              // [nq] query ids for the walk kernel (direct kernel appends)
     unsigned int* work_count;       // number of entries in worklist
     unsigned long long* counters;   // [0] points visited, [1] leaf cells / rows visited, [2] nodes popped (may be null)
@@ -63,11 +67,18 @@ __device__ __forceinline__ float best_ub_cells(double best, double inv_cell2) {
     const double b = best * inv_cell2;
     return (b < 3.0e38) ? __double2float_ru(b) * (1.f + 6e-7f) : FLT_MAX;
 }
+// same for the ball of radius (sqrt(best) + gap): everything inside it gets visited
+__device__ __forceinline__ float best_ub_cells_gap(double best, double inv_cell, float gap_cells) {
+    const double r = sqrt(best) * inv_cell + (double)gap_cells;
+    const double b = r * r;
+    return (b < 3.0e38) ? __double2float_ru(b) * (1.f + 6e-7f) : FLT_MAX;
+}
 
 struct Query {
     double qx, qy, qz;      // FP64 query (oracle order)
     float fx, fy, fz;       // in cell units, FP32 (pruning only)
     double best; int32_t bidx; float bestc;
+    double second;          // smallest exact d2 among visited points other than the current best
     int ilx, ihx, ily, ihy, ilz, ihz;   // level-0 cell span of the ball's bounding cube (valid when has_span)
     bool has_span;
 };
@@ -89,7 +100,8 @@ __device__ __forceinline__ void setup_query(const GridArgs& a, int64_t gq, Query
             Q.bidx = p;
         }
     }
-    Q.bestc = best_ub_cells(Q.best, G.inv_cell * G.inv_cell);
+    Q.bestc = (a.gap_cells > 0.f) ? best_ub_cells_gap(Q.best, G.inv_cell, a.gap_cells) : best_ub_cells(Q.best, G.inv_cell * G.inv_cell);
+    Q.second = INFINITY;
     Q.has_span = false;
     if (Q.bidx >= 0 && Q.bestc < 1.0e12f) {
         // ball radius in cells (upper bound) -> integer cell span
@@ -142,6 +154,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long* counters, uns
 constexpr int GRID_ROW_SPAN = 8;
 constexpr int GRID_FETCH_BATCH = 8;
 
+template <bool COH>
 __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant__ GridArgs a) {
     const GridView& G = a.g;
     const int lane = threadIdx.x & 31;
@@ -172,7 +185,24 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
                 if (cand < end) {
                     gq = cand;
                     setup_query(a, gq, Q);
-                    if (Q.has_span && Q.ihy - Q.ily < GRID_ROW_SPAN && Q.ihz - Q.ilz < GRID_ROW_SPAN && Q.ihx - Q.ilx < 4 * GRID_ROW_SPAN) {
+                    // temporal-coherence certificate: every other model point was at distance >= lb2 before the
+                    // last pose update, which moved this query by at most delta; if the old correspondence is
+                    // now strictly closer than lb2 - delta it is still the unique nearest neighbour.
+                    bool certified = false;
+                    if (COH && a.lb2 && Q.bidx >= 0) {
+                        const float lb_new = __fsub_rd(a.lb2[gq], a.delta[(unsigned)gq / (unsigned)a.ns]);
+                        const float d1 = __double2float_ru(sqrt(Q.best)) * (1.f + 1e-6f) + 1e-30f;
+                        if (d1 < lb_new * (1.f - 1e-6f)) {
+                            certified = true;
+                            a.lb2[gq] = lb_new;
+                            a.idx[gq] = Q.bidx;
+                            if (a.d2) a.d2[gq] = Q.best;
+                            if (a.counters) atomicAdd(&a.counters[3], 1ull);
+                        }
+                    }
+                    if (certified) {
+                        // nothing to scan
+                    } else if (Q.has_span && Q.ihy - Q.ily < GRID_ROW_SPAN && Q.ihz - Q.ilz < GRID_ROW_SPAN && Q.ihx - Q.ilx < 4 * GRID_ROW_SPAN) {
                         x0 = max(Q.ilx, 0); x1 = min(Q.ihx, dx0 - 1);
                         y0 = max(Q.ily, 0); y1 = min(Q.ihy, dy0 - 1);
                         z = max(Q.ilz, 0); z1 = min(Q.ihz, dz0 - 1);
@@ -205,6 +235,12 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
             if (z > z1) {                                    // rows exhausted: done with this query
                 a.idx[gq] = Q.bidx;
                 if (a.d2) a.d2[gq] = Q.best;
+                if (COH && a.lb2) {
+                    // every point within (best distance + gap) was visited: anything else is at least that far
+                    const double r1 = sqrt(Q.best) + (double)a.gap_cells * G.cell;
+                    const double r2 = sqrt(Q.second);
+                    a.lb2[gq] = __double2float_rd(fmin(r1, r2) * (1.0 - 1e-9));
+                }
                 have = false;
             } else {                                         // ROW step
                 float dy2 = axis_lb(Q.fy, (float)y, 1.f);
@@ -232,7 +268,17 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
             const GridPoint gp = G.pts[p];
             ++p;
             const double d = dist2_exact(gp.x, gp.y, gp.z, Q.qx, Q.qy, Q.qz);
-            if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
+            if (COH) {
+                if (gp.orig != Q.bidx) {
+                    if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
+                        Q.second = Q.best;                   // the old best becomes the runner-up
+                        Q.best = d; Q.bidx = gp.orig;
+                        Q.bestc = best_ub_cells_gap(Q.best, G.inv_cell, a.gap_cells);
+                    } else if (d < Q.second) {
+                        Q.second = d;
+                    }
+                }
+            } else if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
                 Q.best = d; Q.bidx = gp.orig;
                 Q.bestc = best_ub_cells(Q.best, inv_cell2);
             }
@@ -325,18 +371,21 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
         }
         a.idx[gq] = Q.bidx;
         if (a.d2) a.d2[gq] = Q.best;
+        if (a.lb2) a.lb2[gq] = 0.f;                          // the walk gives no exhaustive-radius guarantee
     }
     flush_counters(a.counters, n_pts, n_cells, n_nodes);
 }
 
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz, int64_t ns,
                     const double* d_T, int64_t nhyp, const int32_t* d_prev, int32_t* d_idx, double* d_d2,
-                    unsigned long long* d_counters, GridScratch& sc, cudaStream_t st) {
+                    unsigned long long* d_counters, GridScratch& sc, float* d_lb2, const float* d_delta, cudaStream_t st) {
     PCREG_REQUIRE(m->has_grid, "grid NN requested but the model was created without build_grid");
     GridArgs a{};
     a.g = m->grid; a.md = m->md.p;
     a.sx = d_sx; a.sy = d_sy; a.sz = d_sz; a.ns = ns; a.T = d_T; a.nq = nhyp * ns;
     a.prev = d_prev; a.idx = d_idx; a.d2 = d_d2; a.counters = d_counters;
+    a.lb2 = d_lb2; a.delta = d_delta;
+    a.gap_cells = d_lb2 ? 0.15f : 0.f;
     PCREG_REQUIRE(a.nq > 0, "nn_grid: no queries");
     PCREG_REQUIRE(a.nq < 2147483647LL, "nn_grid: too many queries in one launch");
     const int64_t blocks = (a.nq + 127) / 128;
@@ -347,7 +396,8 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
         a.worklist = sc.worklist.p; a.work_count = sc.count.p;
         PCREG_CUDA(cudaMemsetAsync(sc.count.p, 0, sizeof(unsigned int), st));
         const int direct_blocks = (int)std::min<int64_t>(blocks, (int64_t)ctx().sm_count * 16);
-        k_nn_grid_direct<<<direct_blocks, 128, 0, st>>>(a);
+        if (d_lb2) k_nn_grid_direct<true><<<direct_blocks, 128, 0, st>>>(a);
+        else       k_nn_grid_direct<false><<<direct_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
         k_nn_grid_walk<<<walk_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
