@@ -128,6 +128,16 @@ int  pcreg_ransac_score(const double* p1, const double* p2, int64_t P, int64_t l
                         int64_t* max_inl, int64_t* best_hyp,
                         int32_t* inl_counts, int32_t* inl_counts_refined, double* T16_all);
 
+/* The whole ransac.m:21-116 call with the sampling on the device.  MATLAB's global RNG stream
+ * (randperm, ransac.m:42) cannot be matched, so the drop-in defines a documented counter-based sampler:
+ * u_k = splitmix64(seed + 0x9E3779B97F4A7C15 * (3h+k+1)); i0 = u0 mod P, i1 = u1 mod (P-1) skipping i0,
+ * i2 = u2 mod (P-2) skipping both -- a uniformly random ordered 3-subset, like randperm(P)(1:3).
+ * triplets_out (optional, [iter_num][3]) returns the samples that were drawn.  Same outputs / return
+ * value as pcreg_ransac_score. */
+int  pcreg_ransac_run(const double* p1, const double* p2, int64_t P, int64_t ld, int64_t iter_num, uint64_t seed,
+                      const pcreg_ransac_opts* opts, double* T16_best, int32_t* inl_idx, int64_t* n_inl,
+                      int64_t* n_succ, int64_t* max_inl, int64_t* best_hyp, int32_t* triplets_out);
+
 /* ---- batched ICP (composition of quickTF.m, the 85 % trim rule AlignPoints_KNN.m:20-26, the
  *      weights of AlignPoints_weighted.m:16-18, estimateTransform.m:41-71 and ransac.m's
  *      score / first-arg-best structure around an exact NN step) --------- */

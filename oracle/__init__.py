@@ -21,7 +21,7 @@ Parity status (see DESIGN.md section "Oracle"):
 """
 from .primitives import (  # noqa: F401
     eul2rotm, quickTF, invertTF, pcRigidBodyTF, getLocalPoints, getLocalPoints_v2,
-    matlab_round, matlab_rank, estimateTransform, calcDists, ransac, check_alignment,
+    matlab_round, matlab_rank, estimateTransform, calcDists, ransac, ransac_triplets, check_alignment,
 )
 from .align import (  # noqa: F401
     pca_eig, AlignPoints, AlignPoints_KNN, AlignPoints_knn, AlignPoints_weighted,

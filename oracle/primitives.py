@@ -239,6 +239,32 @@ def ransac(pts1, pts2, coef: dict, triplets, reflection_fix: bool = False):
                 best=idx)
 
 
+def _splitmix64(x):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+    return x ^ (x >> np.uint64(31))
+
+
+def ransac_triplets(seed: int, iterNum: int, P: int) -> np.ndarray:
+    """The drop-in's documented stand-in for randperm(ptNum)(1:3) (ransac.m:42-43; MATLAB's RNG stream cannot
+    be matched): restatement of include/pcreg.h pcreg_ransac_run.  Returns int32 [iterNum, 3], 0-based."""
+    with np.errstate(over="ignore"):
+        h = np.arange(iterNum, dtype=np.uint64)
+        g = np.uint64(0x9E3779B97F4A7C15)
+        s = np.uint64(seed & (2 ** 64 - 1))
+        u = [_splitmix64((s + g * (np.uint64(3) * h + np.uint64(k + 1))).astype(np.uint64)) for k in range(3)]
+    i0 = (u[0] % np.uint64(P)).astype(np.int64)
+    i1 = (u[1] % np.uint64(P - 1)).astype(np.int64)
+    i1 = i1 + (i1 >= i0)
+    i2 = (u[2] % np.uint64(P - 2)).astype(np.int64)
+    lo, hi = np.minimum(i0, i1), np.maximum(i0, i1)
+    i2 = i2 + (i2 >= lo)
+    i2 = i2 + (i2 >= hi)
+    return np.stack([i0, i1, i2], axis=1).astype(np.int32)
+
+
 def check_alignment(R1, R2) -> float:
     """checkAlignment, visualizeGTMatches.m:417-421 -- ||R1*R2' - I||_F (success < 0.5, :221)."""
     return float(np.linalg.norm(np.asarray(R1) @ np.asarray(R2).T - np.eye(3), "fro"))

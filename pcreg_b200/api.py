@@ -233,6 +233,33 @@ def ransac(pts1, pts2, coef: dict, triplets, reflection_fix=False, return_all=Fa
     return out
 
 
+def ransac_seeded(pts1, pts2, coef: dict, seed: int = 0, reflection_fix=False, return_triplets=False):
+    """The whole ransac.m call (coef.iterNum samples) with the sampling done on the device by the documented
+    counter-based generator of include/pcreg.h (MATLAB's randperm stream cannot be matched).  Same dict as
+    ransac(); with return_triplets the drawn samples are returned too (0-based [iterNum, 3])."""
+    p1 = np.asfortranarray(np.asarray(pts1, dtype=np.float64))
+    p2 = np.asfortranarray(np.asarray(pts2, dtype=np.float64))
+    P = p1.shape[0]
+    nh = int(coef["iterNum"])
+    o = RansacOpts(float(coef["thDist"]), float(coef["thInlrRatio"]), int(bool(coef.get("REFINE", True))), int(bool(reflection_fix)))
+    Tb = np.empty(16, dtype=np.float64)
+    inl = np.empty(P, dtype=np.int32)
+    n_inl, n_succ, max_inl, best = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    tri = np.empty((nh, 3), dtype=np.int32) if return_triplets else None
+    rc = L.check(L.lib().pcreg_ransac_run(_ptr(p1, L.c_f64p), _ptr(p2, L.c_f64p), P, P, nh, int(seed) & (2 ** 64 - 1), C.byref(o),
+                                          _ptr(Tb, L.c_f64p), _ptr(inl, L.c_i32p), C.byref(n_inl), C.byref(n_succ),
+                                          C.byref(max_inl), C.byref(best), _ptr(tri, L.c_i32p)), "pcreg_ransac_run")
+    out = {}
+    if return_triplets:
+        out["triplets"] = tri
+    if rc != 0:
+        out.update(T=None, inlierIdx=np.zeros(0, dtype=np.int64), numSuccess=0, maxInliers=0, pct=0.0, best=-1)
+    else:
+        out.update(T=_T_from_abi(Tb), inlierIdx=inl[:n_inl.value].astype(np.int64), numSuccess=int(n_succ.value),
+                   maxInliers=int(max_inl.value), pct=100.0 * max_inl.value / P, best=int(best.value))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # batched ICP
 # ------------------------------------------------------------------------------------------------

@@ -274,6 +274,34 @@ __global__ void k_inlier_flags(const double* __restrict__ p1, const double* __re
     flags[i] = dist2_exact(p1[i], p1[ld + i], p1[2 * ld + i], qx, qy, qz) < thDist ? 1 : 0;
 }
 
+// ---- documented counter-based sampler for ransac.m:42-43 (randperm(ptNum) -> first 3) ------------------
+// MATLAB's global RNG stream cannot be matched, so the drop-in defines its own reproducible sampler:
+//   u_k = splitmix64(seed + 0x9E3779B97F4A7C15 * (3*h + k + 1)),  k = 0,1,2
+//   i0 = u_0 mod P;  i1 = u_1 mod (P-1), skipping i0;  i2 = u_2 mod (P-2), skipping both
+// i.e. a uniformly random ORDERED 3-subset without replacement, like the first three entries of randperm.
+// oracle/primitives.py:ransac_triplets restates it in numpy for the parity tests.
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void k_gen_triplets(unsigned long long seed, int64_t nhyp, int64_t P, int32_t* __restrict__ tri) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nhyp) return;
+    const unsigned long long u0 = splitmix64(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(3 * h + 1));
+    const unsigned long long u1 = splitmix64(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(3 * h + 2));
+    const unsigned long long u2 = splitmix64(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(3 * h + 3));
+    const long long i0 = (long long)(u0 % (unsigned long long)P);
+    long long i1 = (long long)(u1 % (unsigned long long)(P - 1));
+    if (i1 >= i0) ++i1;
+    long long i2 = (long long)(u2 % (unsigned long long)(P - 2));
+    const long long lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+    if (i2 >= lo) ++i2;
+    if (i2 >= hi) ++i2;
+    tri[3 * h + 0] = (int32_t)i0; tri[3 * h + 1] = (int32_t)i1; tri[3 * h + 2] = (int32_t)i2;
+}
+
 }  // namespace pcreg
 
 using namespace pcreg;
@@ -311,41 +339,34 @@ int pcreg_kabsch_batch(const double* p1, const double* p2, const double* w, int6
     PCREG_API_END
 }
 
-int pcreg_ransac_score(const double* p1, const double* p2, int64_t P, int64_t ld, const int32_t* triplets, int64_t nhyp,
+// shared body of pcreg_ransac_score / pcreg_ransac_run: triplets already on the device
+static int ransac_core(const double* p1, const double* p2, int64_t P, int64_t ld, const int32_t* d_tri, int64_t nhyp,
                        const pcreg_ransac_opts* opts, double* T16_best, int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ,
-                       int64_t* max_inl, int64_t* best_hyp, int32_t* inl_counts, int32_t* inl_counts_refined, double* T16_all) {
-    PCREG_API_BEGIN
-    require_init();
-    PCREG_REQUIRE(p1 && p2 && triplets && opts && T16_best && inl_idx && n_inl && n_succ && max_inl && best_hyp,
-                  "pcreg_ransac_score: null pointer");
-    PCREG_REQUIRE(P >= 3 && ld >= P && nhyp >= 1, "pcreg_ransac_score: need P >= 3, ld >= P, nhyp >= 1");
-    PCREG_CUDA(cudaSetDevice(ctx().device));
-    cudaStream_t st = 0;
+                       int64_t* max_inl, int64_t* best_hyp, int32_t* inl_counts, int32_t* inl_counts_refined, double* T16_all,
+                       cudaStream_t st) {
     DevBuf<double> d1((size_t)P * 3), d2((size_t)P * 3), dT((size_t)nhyp * 16);
-    DevBuf<int32_t> dtri((size_t)nhyp * 3), dcnt((size_t)nhyp), dcntr((size_t)nhyp);
+    DevBuf<int32_t> dcnt((size_t)nhyp), dcntr((size_t)nhyp);
     for (int a = 0; a < 3; ++a) {
         PCREG_CUDA(cudaMemcpyAsync(d1.p + a * P, p1 + a * ld, (size_t)P * 8, cudaMemcpyHostToDevice, st));
         PCREG_CUDA(cudaMemcpyAsync(d2.p + a * P, p2 + a * ld, (size_t)P * 8, cudaMemcpyHostToDevice, st));
     }
-    PCREG_CUDA(cudaMemcpyAsync(dtri.p, triplets, dtri.bytes(), cudaMemcpyHostToDevice, st));
     RansacArgs a{};
-    a.p1 = d1.p; a.p2 = d2.p; a.P = P; a.ld = P; a.triplets = dtri.p; a.nhyp = nhyp;
+    a.p1 = d1.p; a.p2 = d2.p; a.P = P; a.ld = P; a.triplets = d_tri; a.nhyp = nhyp;
     a.thDist = opts->thDist;
     a.thInlr = floor(opts->thInlrRatio * (double)P + 0.5);            // MATLAB round, ransac.m:28
     a.refine = opts->refine; a.reflection_fix = opts->reflection_fix;
     a.cnt = dcnt.p; a.cnt_ref = dcntr.p; a.T_rm = dT.p;
     const int64_t blocks = (nhyp * 32 + 255) / 256;
-    PCREG_REQUIRE(blocks < 2147483647LL, "pcreg_ransac_score: too many hypotheses");
+    PCREG_REQUIRE(blocks < 2147483647LL, "ransac: too many hypotheses");
     k_ransac_score<<<(unsigned)blocks, 256, 0, st>>>(a);
     PCREG_LAUNCHED();
     std::vector<int32_t> hc((size_t)nhyp), hcr((size_t)nhyp);
     PCREG_CUDA(cudaMemcpyAsync(hc.data(), dcnt.p, dcnt.bytes(), cudaMemcpyDeviceToHost, st));
     PCREG_CUDA(cudaMemcpyAsync(hcr.data(), dcntr.p, dcntr.bytes(), cudaMemcpyDeviceToHost, st));
+    DevBuf<double> dTc(T16_all ? (size_t)nhyp * 16 : 0);
     if (T16_all) {
-        DevBuf<double> dTc((size_t)nhyp * 16);
         transpose16_launch(dT.p, dTc.p, nhyp, st);
         PCREG_CUDA(cudaMemcpyAsync(T16_all, dTc.p, dTc.bytes(), cudaMemcpyDeviceToHost, st));
-        PCREG_CUDA(cudaStreamSynchronize(st));
     }
     PCREG_CUDA(cudaStreamSynchronize(st));
     if (inl_counts) std::copy(hc.begin(), hc.end(), inl_counts);
@@ -374,6 +395,40 @@ int pcreg_ransac_score(const double* p1, const double* p2, int64_t P, int64_t ld
     for (int64_t h = 0; h < nhyp; ++h) ns += ((double)dec[h] >= a.thInlr) ? 1 : 0;       // ransac.m:94-98
     *n_succ = ns; *max_inl = dec[bi]; *best_hyp = bi;
     return PCREG_OK;
+}
+
+int pcreg_ransac_score(const double* p1, const double* p2, int64_t P, int64_t ld, const int32_t* triplets, int64_t nhyp,
+                       const pcreg_ransac_opts* opts, double* T16_best, int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ,
+                       int64_t* max_inl, int64_t* best_hyp, int32_t* inl_counts, int32_t* inl_counts_refined, double* T16_all) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(p1 && p2 && triplets && opts && T16_best && inl_idx && n_inl && n_succ && max_inl && best_hyp,
+                  "pcreg_ransac_score: null pointer");
+    PCREG_REQUIRE(P >= 3 && ld >= P && nhyp >= 1, "pcreg_ransac_score: need P >= 3, ld >= P, nhyp >= 1");
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    cudaStream_t st = 0;
+    DevBuf<int32_t> dtri((size_t)nhyp * 3);
+    PCREG_CUDA(cudaMemcpyAsync(dtri.p, triplets, dtri.bytes(), cudaMemcpyHostToDevice, st));
+    return ransac_core(p1, p2, P, ld, dtri.p, nhyp, opts, T16_best, inl_idx, n_inl, n_succ, max_inl, best_hyp, inl_counts,
+                       inl_counts_refined, T16_all, st);
+    PCREG_API_END
+}
+
+int pcreg_ransac_run(const double* p1, const double* p2, int64_t P, int64_t ld, int64_t iter_num, uint64_t seed,
+                     const pcreg_ransac_opts* opts, double* T16_best, int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ,
+                     int64_t* max_inl, int64_t* best_hyp, int32_t* triplets_out) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(p1 && p2 && opts && T16_best && inl_idx && n_inl && n_succ && max_inl && best_hyp, "pcreg_ransac_run: null pointer");
+    PCREG_REQUIRE(P >= 3 && ld >= P && iter_num >= 1, "pcreg_ransac_run: need P >= 3, ld >= P, iter_num >= 1");
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    cudaStream_t st = 0;
+    DevBuf<int32_t> dtri((size_t)iter_num * 3);
+    k_gen_triplets<<<(unsigned)((iter_num + 255) / 256), 256, 0, st>>>((unsigned long long)seed, iter_num, P, dtri.p);
+    PCREG_LAUNCHED();
+    if (triplets_out) PCREG_CUDA(cudaMemcpyAsync(triplets_out, dtri.p, dtri.bytes(), cudaMemcpyDeviceToHost, st));
+    return ransac_core(p1, p2, P, ld, dtri.p, iter_num, opts, T16_best, inl_idx, n_inl, n_succ, max_inl, best_hyp, nullptr, nullptr,
+                       nullptr, st);
     PCREG_API_END
 }
 

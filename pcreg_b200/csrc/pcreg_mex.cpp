@@ -18,6 +18,8 @@
 //   'estimate_transform', pts1, pts2                   -> T (4x4) or []                      (estimateTransform.m)
 //   'ransac', pts1, pts2, coef(struct), triplets(Hx3, 1-based)
 //                                                      -> T, inlierIdx, numSuccess, maxInliers, pct  (ransac.m)
+//   'ransac_seeded', pts1, pts2, coef(struct incl. iterNum), seed
+//                                                      -> same five outputs, samples drawn on the device (pcreg_ransac_run)
 //   'icp', handle, src(Nx3), T0(4x4xH), opts(struct)[, w_src]
 //                                                      -> T(4x4xH), rmse(Hx1), n_used, status, best(1-based), idx(NxH)
 #include <string.h>
@@ -126,23 +128,33 @@ bool cmd_estimate_transform(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
     return true;
 }
 
-bool cmd_ransac(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+bool cmd_ransac(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], bool seeded) {
     if (nrhs < 5 || !mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || !mxIsStruct(prhs[3]) || !mxIsDouble(prhs[4]) ||
-        mxGetN(prhs[1]) != 3 || mxGetN(prhs[2]) != 3 || mxGetN(prhs[4]) != 3) { g_fail = "ransac: need (pts1, pts2, coef, triplets Hx3)"; return false; }
-    const int64_t P = (int64_t)mxGetM(prhs[1]), H = (int64_t)mxGetM(prhs[4]);
+        mxGetN(prhs[1]) != 3 || mxGetN(prhs[2]) != 3 || (!seeded && mxGetN(prhs[4]) != 3)) {
+        g_fail = "ransac: need (pts1, pts2, coef, triplets Hx3 | seed)";
+        return false;
+    }
+    const int64_t P = (int64_t)mxGetM(prhs[1]);
+    const int64_t H = seeded ? (int64_t)field_or(prhs[3], "iterNum", 1000.0) : (int64_t)mxGetM(prhs[4]);
     pcreg_ransac_opts o;
     o.thDist = field_or(prhs[3], "thDist", 0.5);
     o.thInlrRatio = field_or(prhs[3], "thInlrRatio", 0.1);
     o.refine = field_or(prhs[3], "REFINE", 1.0) != 0;
     o.reflection_fix = 0;
-    std::vector<int32_t> tri((size_t)H * 3), inl((size_t)P);
-    const double* t = mxGetPr(prhs[4]);
-    for (int64_t h = 0; h < H; ++h)
-        for (int k = 0; k < 3; ++k) tri[(size_t)h * 3 + k] = (int32_t)t[k * H + h] - 1;
+    std::vector<int32_t> tri(seeded ? 0 : (size_t)H * 3), inl((size_t)P);
     double T16[16];
     int64_t n_inl = 0, n_succ = 0, max_inl = 0, best = -1;
-    const int rc = pcreg_ransac_score(mxGetPr(prhs[1]), mxGetPr(prhs[2]), P, P, tri.data(), H, &o, T16, inl.data(), &n_inl, &n_succ,
-                                      &max_inl, &best, nullptr, nullptr, nullptr);
+    int rc;
+    if (seeded) {
+        rc = pcreg_ransac_run(mxGetPr(prhs[1]), mxGetPr(prhs[2]), P, P, H, (uint64_t)mxGetScalar(prhs[4]), &o, T16, inl.data(), &n_inl,
+                              &n_succ, &max_inl, &best, nullptr);
+    } else {
+        const double* t = mxGetPr(prhs[4]);
+        for (int64_t h = 0; h < H; ++h)
+            for (int k = 0; k < 3; ++k) tri[(size_t)h * 3 + k] = (int32_t)t[k * H + h] - 1;
+        rc = pcreg_ransac_score(mxGetPr(prhs[1]), mxGetPr(prhs[2]), P, P, tri.data(), H, &o, T16, inl.data(), &n_inl, &n_succ,
+                                &max_inl, &best, nullptr, nullptr, nullptr);
+    }
     if (rc < 0) { g_fail = pcreg_last_error(); return false; }
     if (rc == PCREG_DEGENERATE) {                                       // ransac.m:75-89
         plhs[0] = empty();
@@ -222,7 +234,8 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
         else if (!strcmp(cmd, "nn_search")) ok = cmd_nn_search(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "align")) ok = cmd_align(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "estimate_transform")) ok = cmd_estimate_transform(nlhs, plhs, nrhs, prhs);
-        else if (!strcmp(cmd, "ransac")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "ransac")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs, false);
+        else if (!strcmp(cmd, "ransac_seeded")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs, true);
         else if (!strcmp(cmd, "icp")) ok = cmd_icp(nlhs, plhs, nrhs, prhs);
         else g_fail = std::string("pcreg_mex: unknown command '") + cmd + "'";
     }

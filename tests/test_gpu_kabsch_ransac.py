@@ -112,3 +112,24 @@ def test_ransac_config4_scale_properties(pcreg):
     want = oracle.ransac(p1, p2, coef, tri[sub])
     assert np.array_equal(got["inlrNum"][sub], want["inlrNum"].astype(np.int32))
     assert np.array_equal(got["inlrNum_refined"][sub], want["inlrNum_refined"].astype(np.int32))
+
+
+def test_ransac_seeded_device_sampling_matches_oracle(pcreg):
+    """pcreg_ransac_run: the documented counter-based sampler (include/pcreg.h) drawn on the device equals its
+    numpy restatement, every triplet is 3 distinct in-range indices, and the result equals the oracle ransac on
+    those triplets."""
+    p1, p2, T_true = synth.make_ransac_problem(250, 0.3, 0.1, 77)
+    coef = dict(thDist=0.2, thInlrRatio=0.1, REFINE=True, iterNum=3000)
+    got = pcreg.ransac_seeded(p1, p2, coef, seed=12345, return_triplets=True)
+    tri = oracle.ransac_triplets(12345, 3000, 250)
+    assert np.array_equal(got["triplets"], tri)
+    assert tri.min() >= 0 and tri.max() < 250
+    assert np.all(tri[:, 0] != tri[:, 1]) and np.all(tri[:, 0] != tri[:, 2]) and np.all(tri[:, 1] != tri[:, 2])
+    want = oracle.ransac(p1, p2, coef, tri)
+    assert got["best"] == want["best"] and got["maxInliers"] == want["maxInliers"] and got["numSuccess"] == want["numSuccess"]
+    assert np.array_equal(got["inlierIdx"], want["inlierIdx"])
+    assert np.linalg.norm(got["T"] - want["T"]) < 1e-9
+    # a different seed draws different samples; P = 3 is the smallest legal problem
+    assert not np.array_equal(pcreg.ransac_seeded(p1, p2, coef, seed=1, return_triplets=True)["triplets"], tri)
+    t3 = oracle.ransac_triplets(5, 50, 3)
+    assert np.all(np.sort(t3, axis=1) == np.array([0, 1, 2]))

@@ -144,3 +144,13 @@ def test_icp_oracle_converges_and_golden_is_current():
     assert np.allclose(res["T"], np.asarray(want["T"]), atol=1e-12)
     assert res["best"] == want["best"]
     assert oracle.check_alignment(res["T"][res["best"]][:3, :3], T_gt[:3, :3]) < 0.1
+
+
+def test_ransac_triplets_are_uniform_ordered_subsets():
+    tri = oracle.ransac_triplets(9, 60000, 7)
+    assert tri.min() == 0 and tri.max() == 6
+    assert np.all(tri[:, 0] != tri[:, 1]) and np.all(tri[:, 0] != tri[:, 2]) and np.all(tri[:, 1] != tri[:, 2])
+    # all 7*6*5 = 210 ordered triples occur with roughly equal frequency
+    code = tri[:, 0] * 49 + tri[:, 1] * 7 + tri[:, 2]
+    _, counts = np.unique(code, return_counts=True)
+    assert counts.size == 210 and counts.min() > 0.7 * 60000 / 210 and counts.max() < 1.3 * 60000 / 210
