@@ -73,6 +73,20 @@ int  pcreg_model_grid_info(const pcreg_model* m, int32_t dims[3], double* cell_s
 int  pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t nq, int64_t ld,
                      int nn_kind, int32_t* idx /*[nq]*/, double* d2 /*[nq] squared distance, may be NULL*/);
 
+/* ---- getLocalPoints.m:5-36, batched over centres ------------------------------------------------ */
+/* For each centre c_k (nc x 3 column-major doubles, ld): the model points with vecnorm(p - c_k) < R
+ * (strict), RELATIVE to c_k, in ORIGINAL model order, class double.  Two calls:
+ *   count: counts[k] and status[k] (1 where the reference returns []: count < min_points or > max_points;
+ *          max_points < 0 means inf as in AlignPoints_c.m:14);
+ *   fill : the caller builds offsets[nc+1] (rows of centre k = offsets[k]..offsets[k+1]-1, normally the
+ *          prefix sum of the counts of the centres with status 0, zero-length for the others) and gets
+ *          pts_rel (ntotal x 3 column-major, ld_out), optional dists (vecnorm) and optional original indices. */
+int  pcreg_local_points_count(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, double R,
+                              int64_t min_points, int64_t max_points, int64_t* counts, int32_t* status);
+int  pcreg_local_points_fill(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, double R,
+                             const int64_t* offsets, const int32_t* status, double* pts_rel, int64_t ld_out,
+                             double* dists, int32_t* orig_idx);
+
 /* ---- AlignPoints family (AlignPoints.m:1-29, AlignPoints_KNN.m:1-60, AlignPoints_knn.m:1-43,
  *      AlignPoints_weighted.m:1-49, AlignPoints_c.m:1-44, AlignPoints_KNN_c.m:1-57), batched over
  *      neighbourhoods ---------------------------------------------------------------------------- */

@@ -101,6 +101,52 @@ class Model:
 
 
 # ------------------------------------------------------------------------------------------------
+# getLocalPoints
+# ------------------------------------------------------------------------------------------------
+def getLocalPoints_batch(model: Model, centres, R, min_points, max_points, return_idx=False):
+    """getLocalPoints.m:5-36 for many centres against the resident model: list of (pts_sphere, dists[, idx]) per
+    centre (points relative to the centre, original model order), (None, None) where the reference returns []."""
+    c = np.asfortranarray(np.asarray(centres, dtype=np.float64).reshape(-1, 3))
+    nc = c.shape[0]
+    counts = np.empty(nc, dtype=np.int64)
+    status = np.empty(nc, dtype=np.int32)
+    mx = -1 if max_points is None or np.isinf(max_points) else int(max_points)
+    lib = L.lib()
+    L.check(lib.pcreg_local_points_count(model.handle, _ptr(c, L.c_f64p), nc, nc, float(R), int(min_points), mx,
+                                         _ptr(counts, L.c_i64p), _ptr(status, L.c_i32p)), "pcreg_local_points_count")
+    offsets = np.zeros(nc + 1, dtype=np.int64)
+    np.cumsum(np.where(status == 0, counts, 0), out=offsets[1:])
+    nt = int(offsets[-1])
+    out = np.zeros((max(nt, 1), 3), dtype=np.float64, order="F")
+    dists = np.zeros(max(nt, 1), dtype=np.float64)
+    idx = np.zeros(max(nt, 1), dtype=np.int32) if return_idx else None
+    L.check(lib.pcreg_local_points_fill(model.handle, _ptr(c, L.c_f64p), nc, nc, float(R), _ptr(offsets, L.c_i64p),
+                                        _ptr(status, L.c_i32p), _ptr(out, L.c_f64p), max(nt, 1), _ptr(dists, L.c_f64p),
+                                        _ptr(idx, L.c_i32p)), "pcreg_local_points_fill")
+    res = []
+    for k in range(nc):
+        if status[k] != 0:
+            res.append((None, None, None) if return_idx else (None, None))
+        else:
+            a, b = offsets[k], offsets[k + 1]
+            item = (np.ascontiguousarray(out[a:b]), dists[a:b].copy())
+            res.append(item + (idx[a:b].copy(),) if return_idx else item)
+    return res
+
+
+def getLocalPoints(pts, R, c, min_points, max_points):
+    """getLocalPoints.m:5-36 -> (pts_sphere, dists), or (None, None) for [].  `pts` may be an N x 3 array (uploaded
+    for the call, as the reference signature has it) or a resident Model."""
+    own = not isinstance(pts, Model)
+    m = Model(pts) if own else pts
+    try:
+        return getLocalPoints_batch(m, np.asarray(c, dtype=np.float64).reshape(1, 3), R, min_points, max_points)[0]
+    finally:
+        if own:
+            m.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
 # AlignPoints family
 # ------------------------------------------------------------------------------------------------
 def align_points_batch(kind: int, pts_list, k_frac=0.85, k_abs=500, R_w=3.5, r_local=2.0, min_local=25,

@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpcreg_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["model.cu", "nn_brute.cu", "nn_grid.cu", "icp.cu", "kabsch_ransac.cu", "align.cu"]
-HEADERS = ["pcreg_internal.h", "pcreg_dev.cuh", "pcreg_math.cuh", os.path.join("..", "..", "include", "pcreg.h")]
+SOURCES = ["model.cu", "nn_brute.cu", "nn_grid.cu", "icp.cu", "kabsch_ransac.cu", "align.cu", "local_points.cu"]
+HEADERS = ["pcreg_internal.h", "pcreg_dev.cuh", "pcreg_math.cuh", "pcreg_select.cuh", os.path.join("..", "..", "include", "pcreg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -55,7 +55,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(6, len(srcs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
