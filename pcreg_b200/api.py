@@ -351,7 +351,7 @@ def last_profile() -> dict:
     v = list(buf)
     return dict(nn_launches=v[0], nn_ms=v[1], nn_queries=v[2], brute_pairs=v[3], update_launches=v[4],
                 update_ms=v[5], correspondences=v[6], grid_points_visited=v[7], grid_cells_visited=v[8],
-                grid_nodes_popped=v[9], certified_queries=v[10])
+                grid_nodes_popped=v[9], certified_queries=v[10], walked_queries=v[11], rowscan_queries=v[12])
 
 
 def launch_count() -> int:

@@ -344,8 +344,10 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     for (int i = 0; i < 16; ++i) c.profile[i] = 0.0;
 
     // chunk the hypotheses so that the per-correspondence scratch stays bounded
-    const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0));
-    const size_t budget = (size_t)3 << 30;
+    size_t free_b = 0, total_b = 0;
+    PCREG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + 24 + 4 * 64 + 4 * 448 / 16 : 0));
+    const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)24 << 30, total_b / 6));
     int64_t hc = (int64_t)std::max<size_t>(1, budget / per_hyp);
     hc = std::min(hc, nhyp);
     hc = std::min<int64_t>(hc, 2147483647LL / std::max<int64_t>(1, ns) );       // int32 grid.x of per-query kernels stays safe
@@ -358,16 +360,22 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     DevBuf<int32_t> frozen((size_t)nhyp);
     DevBuf<double> rmse_tmp(d_rmse ? 0 : (size_t)nhyp);
     DevBuf<int32_t> nused_tmp(d_n_used ? 0 : (size_t)nhyp);
-    DevBuf<unsigned long long> counters(4);
+    DevBuf<unsigned long long> counters(8);
     NNScratch scratch;
     GridScratch gscratch;
-    // temporal coherence (grid NN): per-query lower bound of the runner-up distance, per-hypothesis motion bound
-    // EXPERIMENTAL, off by default (PCREG_COHERENCE=1): on C3 only ~20-30 % of the steady-state queries certify
-    // (the runner-up is typically 0.02 mm away, the pose drifts 0.005-0.015 mm per iteration) and the larger
-    // exhaustive radius costs more than the skipped searches save (profiles/r01_notes.md).
-    static const bool coherence_on = [] { const char* e = getenv("PCREG_COHERENCE"); return e && e[0] == '1'; }();
-    const bool coherent = (o.nn == PCREG_NN_GRID) && coherence_on;
-    DevBuf<float> lb2(coherent ? (size_t)hc * ns : 0), delta(coherent ? (size_t)nhyp : 0);
+    // candidate lists (grid NN, nn_grid.cu): built by the full searches once a pose has nearly stopped moving,
+    // scanned instead of searching while the query stays inside its list's guarantee.  PCREG_LISTS=0 disables.
+    static const bool lists_on = [] { const char* e = getenv("PCREG_LISTS"); return !(e && e[0] == '0'); }();
+    static const double list_skin_cells = [] { const char* e = getenv("PCREG_LIST_SKIN"); return e ? atof(e) : 0.6; }();
+    static const int list_cap = [] { const char* e = getenv("PCREG_LIST_CAP"); int v = e ? atoi(e) : 64; return std::max(4, (v + 3) & ~3); }();
+    const bool use_lists = (o.nn == PCREG_NN_GRID) && lists_on && o.iters >= 3;
+    DevBuf<float4> cl_hdr(use_lists ? (size_t)hc * ns : 0);
+    DevBuf<int32_t> cl_cnt(use_lists ? (size_t)hc * ns : 0), cl_list(use_lists ? (size_t)hc * ns * list_cap : 0);
+    DevBuf<float> delta(use_lists ? (size_t)nhyp : 0);
+    const int ext_cap = 448;                                               // wide balls: up to list_cap + 448 candidates
+    const int64_t ext_slots = use_lists ? std::max<int64_t>(1024, hc * ns / 16) : 0;
+    DevBuf<int32_t> cl_ext(use_lists ? (size_t)hc * ns : 0), cl_ext_list((size_t)ext_slots * ext_cap);
+    DevBuf<unsigned int> cl_ext_count(use_lists ? 1 : 0);
     DevBuf<double> src_stats(4);
     double* rm = d_rmse ? d_rmse : rmse_tmp.p;
     int32_t* nu = d_n_used ? d_n_used : nused_tmp.p;
@@ -403,13 +411,27 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     const double* sx = d_src; const double* sy = d_src + ns; const double* sz = d_src + 2 * ns;
     k_src_stats<<<1, 1024, 0, st>>>(d_src, ns, src_stats.p);
     PCREG_LAUNCHED();
-    if (coherent) PCREG_CUDA(cudaMemsetAsync(delta.p, 0, delta.bytes(), st));
+    CandView cl{};
+    if (use_lists) {
+        cl.hdr = cl_hdr.p; cl.cnt = cl_cnt.p; cl.list = cl_list.p; cl.cap = list_cap;
+        cl.ext = cl_ext.p; cl.ext_list = cl_ext_list.p; cl.ext_count = cl_ext_count.p; cl.ext_cap = ext_cap; cl.ext_slots = (int32_t)ext_slots;
+        cl.gap_cells = (float)list_skin_cells;
+        cl.skin = (double)cl.gap_cells * m->grid.cell * (1.0 - 1e-6);
+        static const double build_frac = [] { const char* e = getenv("PCREG_LIST_BUILD"); return e ? atof(e) : 1.0; }();
+        cl.build_max_delta = (float)(build_frac * cl.skin);
+        PCREG_CUDA(cudaMemsetAsync(delta.p, 0x7f, delta.bytes(), st));      // "large" until the first update writes it
+    }
     double nn_launches = 0, upd_launches = 0;
     for (int64_t h0 = 0; h0 < nhyp; h0 += hc) {
         const int64_t hn = std::min(hc, nhyp - h0);
         int32_t* cur = idxA.p; int32_t* prev = idxB.p;
         bool have_prev = false;
-        if (coherent) PCREG_CUDA(cudaMemsetAsync(lb2.p, 0, (size_t)hn * ns * sizeof(float), st));
+        if (use_lists) {
+            PCREG_CUDA(cudaMemsetAsync(cl_cnt.p, 0xff, (size_t)hn * ns * sizeof(int32_t), st));     // -1: no list yet
+            PCREG_CUDA(cudaMemsetAsync(cl_ext.p, 0xff, (size_t)hn * ns * sizeof(int32_t), st));     // -1: no extension slot
+            PCREG_CUDA(cudaMemsetAsync(cl_ext_count.p, 0, sizeof(unsigned int), st));
+            cl.delta = delta.p + h0;
+        }
         for (int it = 0; it <= o.iters; ++it) {
             const bool last = (it == o.iters);
             int32_t* out_idx = (last && d_idx && !sorted) ? d_idx + h0 * ns : cur;
@@ -418,7 +440,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
                 nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p, scratch, st);
             else
                 nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p,
-                               prof ? counters.p : nullptr, gscratch, coherent ? lb2.p : nullptr, coherent ? delta.p + h0 : nullptr, st);
+                               prof ? counters.p : nullptr, gscratch, use_lists ? &cl : nullptr, it >= 2, st);
             ev_end();
             nn_launches += 1;
             IcpUpdateArgs ua{};
@@ -427,7 +449,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             ua.sx = sx; ua.sy = sy; ua.sz = sz; ua.w_src = d_w; ua.ns = ns;
             ua.T = Twork.p + h0 * 16; ua.idx = out_idx; ua.d2 = d2.p; ua.keys = keys.p;
             ua.tie_order = sorted ? sinv.p : nullptr;
-            ua.delta = coherent ? delta.p + h0 : nullptr;
+            ua.delta = use_lists ? delta.p + h0 : nullptr;
             ua.src_stats = src_stats.p;
             ua.mode = o.mode; ua.k_frac = o.k_frac; ua.R_w = o.R_w; ua.thDist2 = o.thDist2; ua.reflection_fix = o.reflection_fix;
             ua.update = last ? 0 : 1;
@@ -460,9 +482,9 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             (e.kind == 0 ? nn_ms : upd_ms) += ms;
             if (debug_times()) fprintf(stderr, "[pcreg] %s %.3f ms\n", e.kind == 0 ? "nn" : "update", ms);
         }
-        unsigned long long hcnt[4] = {0, 0, 0, 0};
+        unsigned long long hcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
-        c.profile[10] = (double)hcnt[3];
+        c.profile[10] = (double)hcnt[3]; c.profile[11] = (double)hcnt[4]; c.profile[12] = (double)hcnt[5];
         const double nq = (double)nhyp * (double)ns * (double)(o.iters + 1);
         c.profile[0] = nn_launches; c.profile[1] = nn_ms; c.profile[2] = nq;
         c.profile[3] = (o.nn == PCREG_NN_BRUTE) ? nq * (double)m->n : 0.0;
@@ -552,7 +574,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
     const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     DevBuf<double> d_q((size_t)nq * 3), d_T(16), d_d2((size_t)nq);
     DevBuf<int32_t> d_idx((size_t)nq);
-    DevBuf<unsigned long long> counters(4);
+    DevBuf<unsigned long long> counters(8);
     NNScratch scratch;
     GridScratch gscratch;
     PCREG_CUDA(cudaMemcpyAsync(d_q.p, hq.data(), d_q.bytes(), cudaMemcpyHostToDevice, st));
@@ -564,7 +586,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         nn_brute_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p, scratch, st);
     else
         nn_grid_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p,
-                       c.profiling ? counters.p : nullptr, gscratch, nullptr, nullptr, st);
+                       c.profiling ? counters.p : nullptr, gscratch, nullptr, false, st);
     if (c.profiling) PCREG_CUDA(cudaEventRecord(e1, st));
     PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
     if (d2) PCREG_CUDA(cudaMemcpyAsync(d2, d_d2.p, d_d2.bytes(), cudaMemcpyDeviceToHost, st));
@@ -573,7 +595,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         float ms = 0.f;
         PCREG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         cudaEventDestroy(e0); cudaEventDestroy(e1);
-        unsigned long long hcnt[4] = {0, 0, 0, 0};
+        unsigned long long hcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
         c.profile[0] = 1; c.profile[1] = ms; c.profile[2] = (double)nq;
         c.profile[3] = nn_kind == PCREG_NN_BRUTE ? (double)nq * (double)m->n : 0.0;

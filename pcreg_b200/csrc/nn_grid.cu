@@ -4,11 +4,18 @@
 // reference's nearest analogue of a spatially pruned search is speedyDescriptors.m:44-60 (boxes with a
 // halo) and getLocalPoints.m:8-15 (cube pre-filter).
 //
-// Two kernels per NN pass, one thread per query in both:
+// Up to three kernels per NN pass, one thread per query in each:
+//   k_nn_list         (ICP passes >= 2) queries that own a CANDIDATE LIST -- every model point within
+//                     R_list = r0 + skin of the position q0 the query had when the list was built -- scan it
+//                     exactly.  A point outside the list is farther than R_list - |q - q0| from the moved
+//                     query, so when the best list distance is below that the list answer is the exact
+//                     nearest neighbour (ties included).  Everything else goes to the next kernel.
 //   k_nn_grid_direct  warm-started queries whose ball (radius = distance to the previous iteration's
 //                     correspondence) has a bounding cube of at most 4 x 4 x 4 level-0 cells: the <= 16
 //                     (y,z) cell rows are contiguous point runs, fetched with independent loads and
 //                     scanned.  Everything else is appended to a work list (warp-aggregated atomics).
+//                     BUILD variant: the scan is exhaustive within (best distance + gap) and the points within
+//                     (best distance + skin) become the query's new candidate list.
 //   k_nn_grid_walk    branch-and-bound walk of the occupancy pyramid with a small explicit stack for the
 //                     work list (far queries, and every query of the first iteration).  Keeping the two
 //                     populations in separate launches keeps the lanes of a warp on similar work.
@@ -18,6 +25,7 @@
 // (d2, original index) -- the answer equals the FP64 brute-force answer bit for bit.
 #include <math.h>
 #include <float.h>
+#include <stdlib.h>
 #include <algorithm>
 
 #include "pcreg_internal.h"
@@ -32,13 +40,15 @@ struct GridArgs {
     const double* T; int64_t nq;
     const int32_t* prev;
     int32_t* idx; double* d2;
-    float* lb2;                     // [nq] in/out or null: lower bound of the distance from the query to every model point
-                                    //      OTHER than its correspondence (temporal-coherence certificate, see below)
-    const float* delta;             // [nhyp] or null: upper bound of how far the last pose update moved any source point
-    float gap_cells;                // the row scan is exhaustive within (best distance + gap), in cell units
-    int32_t* worklist;              // [nq] query ids for the walk kernel (direct kernel appends)
+    CandView cl;                    // candidate lists of the chunk (cl.cnt == nullptr: disabled)
+    const int32_t* in_list;         // direct kernel: the queries to process (nullptr: all nq)
+    const unsigned int* in_count;   //                and how many
+    int32_t* worklist;              // [nq] query ids handed to the next kernel (list -> direct -> walk)
     unsigned int* work_count;       // number of entries in worklist
-    unsigned long long* counters;   // [0] points visited, [1] leaf cells / rows visited, [2] nodes popped (may be null)
+    int row_span;                   // direct kernel: widest (y,z) cell span it row-scans itself
+    unsigned long long* counters;   // [0] points visited, [1] leaf cells / rows visited, [2] nodes popped,
+                                    // [3] queries answered from their candidate list, [4] queries walked,
+                                    // [5] queries row-scanned (may be null)
 };
 
 constexpr int GRID_STACK = 80;
@@ -78,12 +88,11 @@ struct Query {
     double qx, qy, qz;      // FP64 query (oracle order)
     float fx, fy, fz;       // in cell units, FP32 (pruning only)
     double best; int32_t bidx; float bestc;
-    double second;          // smallest exact d2 among visited points other than the current best
     int ilx, ihx, ily, ihy, ilz, ihz;   // level-0 cell span of the ball's bounding cube (valid when has_span)
     bool has_span;
 };
 
-__device__ __forceinline__ void setup_query(const GridArgs& a, int64_t gq, Query& Q) {
+__device__ __forceinline__ void setup_query(const GridArgs& a, int64_t gq, Query& Q, float gap_cells, int32_t warm) {
     const GridView& G = a.g;
     const unsigned h = (unsigned)gq / (unsigned)a.ns, i = (unsigned)gq - h * (unsigned)a.ns;      // nq < 2^31 (launcher)
     quick_tf(a.T + (size_t)h * 16, a.sx[i], a.sy[i], a.sz[i], Q.qx, Q.qy, Q.qz);
@@ -92,16 +101,12 @@ __device__ __forceinline__ void setup_query(const GridArgs& a, int64_t gq, Query
     Q.fz = __double2float_rn((Q.qz - G.origin[2]) * G.inv_cell);
     Q.best = INFINITY;
     Q.bidx = -1;
-    if (a.prev) {
-        const int32_t p = a.prev[gq];
-        if (p >= 0) {
-            const ModelPointD mp = a.md[p];
-            Q.best = dist2_exact(mp.x, mp.y, mp.z, Q.qx, Q.qy, Q.qz);
-            Q.bidx = p;
-        }
+    if (warm >= 0) {                 // any model point bounds the answer: the caller's previous correspondence, or a neighbour's
+        const ModelPointD mp = a.md[warm];
+        Q.best = dist2_exact(mp.x, mp.y, mp.z, Q.qx, Q.qy, Q.qz);
+        Q.bidx = warm;
     }
-    Q.bestc = (a.gap_cells > 0.f) ? best_ub_cells_gap(Q.best, G.inv_cell, a.gap_cells) : best_ub_cells(Q.best, G.inv_cell * G.inv_cell);
-    Q.second = INFINITY;
+    Q.bestc = (gap_cells > 0.f) ? best_ub_cells_gap(Q.best, G.inv_cell, gap_cells) : best_ub_cells(Q.best, G.inv_cell * G.inv_cell);
     Q.has_span = false;
     if (Q.bidx >= 0 && Q.bestc < 1.0e12f) {
         // ball radius in cells (upper bound) -> integer cell span
@@ -151,18 +156,66 @@ __device__ __forceinline__ void flush_counters(unsigned long long* counters, uns
 // row"; a lane that finishes its query takes the next one of the warp's range.  Fetching (pose transform,
 // warm-start bound) is batched: it runs only when >= GRID_FETCH_BATCH lanes are idle, so it executes with
 // many active lanes too.
-constexpr int GRID_ROW_SPAN = 8;
+constexpr int GRID_ROW_SPAN = 12;
 constexpr int GRID_FETCH_BATCH = 8;
 
-template <bool COH>
+// (sqrt(best) + skin)^2, never too small: the points with d2 <= this value enter the candidate list
+__device__ __forceinline__ double list_thr2(double best, double skin) {
+    const double t = sqrt(best) + skin;
+    return t * t * (1.0 + 1e-12);
+}
+// warp-aggregated append of query ids to the next kernel's work list
+__device__ __forceinline__ void worklist_append(const GridArgs& a, bool defer, int64_t gq, int lane) {
+    const unsigned dm = __ballot_sync(0xffffffffu, defer);
+    if (dm) {
+        const int leader = __ffs(dm) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(a.work_count, (unsigned)__popc(dm));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (defer) a.worklist[base + __popc(dm & ((1u << lane) - 1u))] = (int32_t)gq;
+    }
+}
+
+// append grid position p to the list under construction: the first cl.cap entries live in the query's own
+// row, longer lists (wide balls) continue in an extension slot taken from a shared pool on first need
+__device__ __forceinline__ void list_append(const CandView& cl, int64_t gq, int& lc, int& ext_slot, int32_t p) {
+    if (lc < cl.cap) {
+        cl.list[gq * cl.cap + lc] = p;
+    } else {
+        if (ext_slot == -1) {
+            const unsigned s = atomicAdd(cl.ext_count, 1u);
+            ext_slot = s < (unsigned)cl.ext_slots ? (int)s : -2;          // -2: pool exhausted
+        }
+        const int k = lc - cl.cap;
+        if (ext_slot >= 0 && k < cl.ext_cap) cl.ext_list[(int64_t)ext_slot * cl.ext_cap + k] = p;
+    }
+    ++lc;
+}
+// close the list of a finished search: header + count, or "no list"
+__device__ __forceinline__ void list_commit(const CandView& cl, const GridView& G, int64_t gq, const Query& Q, bool bld, int lc, int ext_slot) {
+    if (ext_slot >= 0) cl.ext[gq] = ext_slot;
+    if (bld && lc > 0 && (lc <= cl.cap || (ext_slot >= 0 && lc <= cl.cap + cl.ext_cap))) {
+        // every model point within R_list of this position is in the list
+        const double rl = (sqrt(Q.best) + cl.skin) * (1.0 - 1e-7);
+        cl.hdr[gq] = make_float4(__double2float_rn(Q.qx - G.origin[0]), __double2float_rn(Q.qy - G.origin[1]),
+                                 __double2float_rn(Q.qz - G.origin[2]), __double2float_rd(rl));
+        cl.cnt[gq] = lc;
+    } else {
+        cl.cnt[gq] = -1;
+    }
+}
+
+template <bool BUILD>
 __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant__ GridArgs a) {
     const GridView& G = a.g;
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t per_warp = (a.nq + nwarps - 1) / nwarps;
+    const int64_t total = a.in_list ? (int64_t)*a.in_count : a.nq;
+    if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters[5], (unsigned long long)total);
+    const int64_t per_warp = (total + nwarps - 1) / nwarps;
     int64_t next = warp_id * per_warp;                       // warp-uniform cursor into this warp's range
-    const int64_t end = min(a.nq, next + per_warp);
+    const int64_t end = min(total, next + per_warp);
     const double inv_cell2 = G.inv_cell * G.inv_cell;
     const int dx0 = G.dims[0][0], dy0 = G.dims[0][1], dz0 = G.dims[0][2];
     unsigned long long n_pts = 0, n_cells = 0;
@@ -173,6 +226,10 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0, z1 = 0, y = 0, z = 0;
     int32_t p = 0, e = 0;
     float dz2 = 0.f;
+    // candidate-list construction (BUILD)
+    bool bld = false;
+    int lc = 0, ext_slot = -1;
+    double thr2 = 0.0;
 
     while (true) {
         // ---- batched fetch ----
@@ -183,26 +240,15 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
             if (!have) {
                 const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
                 if (cand < end) {
-                    gq = cand;
-                    setup_query(a, gq, Q);
-                    // temporal-coherence certificate: every other model point was at distance >= lb2 before the
-                    // last pose update, which moved this query by at most delta; if the old correspondence is
-                    // now strictly closer than lb2 - delta it is still the unique nearest neighbour.
-                    bool certified = false;
-                    if (COH && a.lb2 && Q.bidx >= 0) {
-                        const float lb_new = __fsub_rd(a.lb2[gq], a.delta[(unsigned)gq / (unsigned)a.ns]);
-                        const float d1 = __double2float_ru(sqrt(Q.best)) * (1.f + 1e-6f) + 1e-30f;
-                        if (d1 < lb_new * (1.f - 1e-6f)) {
-                            certified = true;
-                            a.lb2[gq] = lb_new;
-                            a.idx[gq] = Q.bidx;
-                            if (a.d2) a.d2[gq] = Q.best;
-                            if (a.counters) atomicAdd(&a.counters[3], 1ull);
-                        }
+                    gq = a.in_list ? (int64_t)a.in_list[cand] : cand;
+                    float gap = 0.f;
+                    if (BUILD) {
+                        // a list pays only if the pose has (nearly) stopped moving
+                        bld = !a.cl.delta || a.cl.delta[(unsigned)gq / (unsigned)a.ns] <= a.cl.build_max_delta;
+                        gap = bld ? a.cl.gap_cells : 0.f;
                     }
-                    if (certified) {
-                        // nothing to scan
-                    } else if (Q.has_span && Q.ihy - Q.ily < GRID_ROW_SPAN && Q.ihz - Q.ilz < GRID_ROW_SPAN && Q.ihx - Q.ilx < 4 * GRID_ROW_SPAN) {
+                    setup_query(a, gq, Q, gap, a.prev[gq]);
+                    if (Q.has_span && Q.ihy - Q.ily < a.row_span && Q.ihz - Q.ilz < a.row_span && Q.ihx - Q.ilx < 4 * a.row_span) {
                         x0 = max(Q.ilx, 0); x1 = min(Q.ihx, dx0 - 1);
                         y0 = max(Q.ily, 0); y1 = min(Q.ihy, dy0 - 1);
                         z = max(Q.ilz, 0); z1 = min(Q.ihz, dz0 - 1);
@@ -212,21 +258,14 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
                         const float t = axis_lb(Q.fz, (float)z, 1.f);
                         dz2 = t * t;
                         have = true;
+                        if (BUILD) { lc = 0; ext_slot = bld ? a.cl.ext[gq] : -1; thr2 = bld ? list_thr2(Q.best, a.cl.skin) : 0.0; }
                     } else {
                         defer = true;
                     }
                 }
             }
             next += nidle;
-            // deferred queries go to the walk kernel's work list (warp-aggregated append)
-            const unsigned dm = __ballot_sync(0xffffffffu, defer);
-            if (dm) {
-                const int leader = __ffs(dm) - 1;
-                unsigned base = 0;
-                if (lane == leader) base = atomicAdd(a.work_count, (unsigned)__popc(dm));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (defer) a.worklist[base + __popc(dm & ((1u << lane) - 1u))] = (int32_t)gq;
-            }
+            worklist_append(a, defer, gq, lane);             // deferred queries go to the walk kernel
             continue;
         }
         if (nidle == 32) break;                              // nothing in flight and nothing left to fetch
@@ -235,12 +274,7 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
             if (z > z1) {                                    // rows exhausted: done with this query
                 a.idx[gq] = Q.bidx;
                 if (a.d2) a.d2[gq] = Q.best;
-                if (COH && a.lb2) {
-                    // every point within (best distance + gap) was visited: anything else is at least that far
-                    const double r1 = sqrt(Q.best) + (double)a.gap_cells * G.cell;
-                    const double r2 = sqrt(Q.second);
-                    a.lb2[gq] = __double2float_rd(fmin(r1, r2) * (1.0 - 1e-9));
-                }
+                if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, ext_slot);
                 have = false;
             } else {                                         // ROW step
                 float dy2 = axis_lb(Q.fy, (float)y, 1.f);
@@ -266,70 +300,169 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
         }
         if (have && p < e) {                                 // POINT step
             const GridPoint gp = G.pts[p];
-            ++p;
             const double d = dist2_exact(gp.x, gp.y, gp.z, Q.qx, Q.qy, Q.qz);
-            if (COH) {
-                if (gp.orig != Q.bidx) {
-                    if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
-                        Q.second = Q.best;                   // the old best becomes the runner-up
-                        Q.best = d; Q.bidx = gp.orig;
-                        Q.bestc = best_ub_cells_gap(Q.best, G.inv_cell, a.gap_cells);
-                    } else if (d < Q.second) {
-                        Q.second = d;
-                    }
-                }
-            } else if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
+            if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
                 Q.best = d; Q.bidx = gp.orig;
-                Q.bestc = best_ub_cells(Q.best, inv_cell2);
+                if (BUILD && bld) {
+                    Q.bestc = best_ub_cells_gap(Q.best, G.inv_cell, a.cl.gap_cells);
+                    thr2 = list_thr2(Q.best, a.cl.skin);
+                } else {
+                    Q.bestc = best_ub_cells(Q.best, inv_cell2);
+                }
             }
+            if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p);
+            ++p;
         }
     }
     flush_counters(a.counters, n_pts, n_cells, 0);
 }
 
-// ---- kernel 2: pyramid walk over the work list (worklist == nullptr: every query) ---------------------------
+// ---- kernel 0: candidate-list scan -------------------------------------------------------------------------
+// Latency-bound by construction (count -> list entries in HBM -> model points in L2), so the loads are software
+// pipelined: the first 8 entries are requested together with the count and the header, the next 8 while the
+// current 8 points are in flight.
+struct GP4 { double x, y, z; long long w; };     // one GridPoint as four 64-bit registers (orig in the low word of w)
+__device__ __forceinline__ GP4 ldg_point(const GridPoint* p) {
+    GP4 r;
+    // one 256-bit load; volatile so that the eight gathers of a batch are issued back to back
+    asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=l"(r.w) : "l"(p));
+    return r;
+}
+struct ListScan {
+    double qx, qy, qz, best;
+    int32_t bidx;
+    __device__ __forceinline__ void eval8(const GridPoint* __restrict__ pts, const int4& ea, const int4& eb, int n) {
+        // n = valid entries among the 8 (>= 1); invalid ones repeat entry 0 (harmless)
+        const int p0 = ea.x, p1 = n > 1 ? ea.y : p0, p2 = n > 2 ? ea.z : p0, p3 = n > 3 ? ea.w : p0;
+        const int p4 = n > 4 ? eb.x : p0, p5 = n > 5 ? eb.y : p0, p6 = n > 6 ? eb.z : p0, p7 = n > 7 ? eb.w : p0;
+        const GP4 g0 = ldg_point(pts + p0), g1 = ldg_point(pts + p1), g2 = ldg_point(pts + p2), g3 = ldg_point(pts + p3);
+        const GP4 g4 = ldg_point(pts + p4), g5 = ldg_point(pts + p5), g6 = ldg_point(pts + p6), g7 = ldg_point(pts + p7);
+        take(g0); take(g1); take(g2); take(g3); take(g4); take(g5); take(g6); take(g7);
+    }
+    __device__ __forceinline__ void take(const GP4& g) {
+        const double d = dist2_exact(g.x, g.y, g.z, qx, qy, qz);
+        const int32_t orig = (int32_t)(g.w & 0xffffffffll);
+        if (d < best || (d == best && orig < bidx)) { best = d; bidx = orig; }
+    }
+};
+
+__global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArgs a) {
+    const GridView& G = a.g;
+    const int lane = threadIdx.x & 31;
+    const int64_t gq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool defer = false, done = false;
+    if (gq < a.nq) {
+        const int4* __restrict__ L4 = reinterpret_cast<const int4*>(a.cl.list + gq * a.cl.cap);
+        const int cnt = a.cl.cnt[gq];
+        int4 na = L4[0], nb = L4[1];                  // requested before cnt is known (rows are allocated either way)
+        const float4 hd = a.cl.hdr[gq];
+        if (cnt <= 0) {
+            defer = true;
+        } else {
+            const unsigned h = (unsigned)gq / (unsigned)a.ns, i = (unsigned)gq - h * (unsigned)a.ns;
+            ListScan S;
+            quick_tf(a.T + (size_t)h * 16, a.sx[i], a.sy[i], a.sz[i], S.qx, S.qy, S.qz);
+            S.best = INFINITY; S.bidx = -1;
+            const int nbase = min(cnt, a.cl.cap);
+            for (int k = 0; k < nbase; k += 8) {
+                const int4 ea = na, eb = nb;
+                if (k + 8 < nbase) { na = L4[(k >> 2) + 2]; nb = L4[(k >> 2) + 3]; }
+                S.eval8(G.pts, ea, eb, nbase - k);
+            }
+            if (cnt > a.cl.cap) {
+                const int4* __restrict__ E4 = reinterpret_cast<const int4*>(a.cl.ext_list + (int64_t)a.cl.ext[gq] * a.cl.ext_cap);
+                const int next = cnt - a.cl.cap;
+                na = E4[0]; nb = E4[1];
+                for (int k = 0; k < next; k += 8) {
+                    const int4 ea = na, eb = nb;
+                    if (k + 8 < next) { na = E4[(k >> 2) + 2]; nb = E4[(k >> 2) + 3]; }
+                    S.eval8(G.pts, ea, eb, next - k);
+                }
+            }
+            // upper bound of |q - q0| (q0 = position when the list was built; both rounded to FP32 here)
+            const float fx = __double2float_rn(S.qx - G.origin[0]), fy = __double2float_rn(S.qy - G.origin[1]), fz = __double2float_rn(S.qz - G.origin[2]);
+            const float ex = fx - hd.x, ey = fy - hd.y, ez = fz - hd.z;
+            float moved = __fsqrt_ru(__fmaf_ru(ex, ex, __fmaf_ru(ey, ey, __fmul_ru(ez, ez))));
+            moved = moved * (1.f + 1e-6f) + 3e-7f * (fabsf(fx) + fabsf(fy) + fabsf(fz) + fabsf(hd.x) + fabsf(hd.y) + fabsf(hd.z)) + 1e-30f;
+            // a model point outside the list is farther than R_list - moved from q: is the list's best closer?
+            const float r1 = __fsqrt_ru(__double2float_ru(S.best));
+            if (__fadd_ru(r1, moved) * (1.f + 1e-6f) < hd.w) {
+                a.idx[gq] = S.bidx;
+                if (a.d2) a.d2[gq] = S.best;
+                done = true;
+            } else {
+                defer = true;
+            }
+        }
+    }
+    worklist_append(a, defer, gq, lane);
+    if (a.counters) {
+        const unsigned dm = __ballot_sync(0xffffffffu, done);
+        if (lane == 0 && dm) atomicAdd(&a.counters[3], (unsigned long long)__popc(dm));
+    }
+}
+
+// ---- kernel 2: pyramid walk --------------------------------------------------------------------------------
+// worklist != nullptr: the queries the direct kernel handed over (wide balls), warm-started by the caller's previous
+// correspondences.  worklist == nullptr (first ICP pass, pcreg_nn_search): EVERY query, in chains of WALK_CHAIN
+// consecutive queries per thread -- the source cloud is spatially sorted, so the answer of one query is a tight
+// bound for the next and only the first query of a chain descends from the root.
+constexpr int WALK_CHAIN = 8;
+
+template <bool BUILD>
 __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ GridArgs a) {
     const GridView& G = a.g;
-    const int64_t count = a.worklist ? (int64_t)*a.work_count : a.nq;
+    const bool chained = (a.worklist == nullptr);
+    const int64_t count = chained ? (a.nq + WALK_CHAIN - 1) / WALK_CHAIN : (int64_t)*a.work_count;
+    if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters[4], (unsigned long long)(chained ? a.nq : count));
     const double inv_cell2 = G.inv_cell * G.inv_cell;
     unsigned long long n_pts = 0, n_cells = 0, n_nodes = 0;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < count; w += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t gq = a.worklist ? (int64_t)a.worklist[w] : w;
-        Query Q;
-        setup_query(a, gq, Q);
-        const float fx = Q.fx, fy = Q.fy, fz = Q.fz;
-        unsigned long long stack[GRID_STACK];
-        int sp = 0;
-        const int top = G.nlevels - 1;
-        bool from_root = true;
-        if (Q.has_span) {
-            // lowest level whose <= 2 x 2 x 2 nodes cover the ball's bounding cube
-            int l = 0;
-            while (l < top && (((Q.ihx >> l) - (Q.ilx >> l)) > 1 || ((Q.ihy >> l) - (Q.ily >> l)) > 1 || ((Q.ihz >> l) - (Q.ilz >> l)) > 1)) ++l;
-            if (((Q.ihx >> l) - (Q.ilx >> l)) <= 1 && ((Q.ihy >> l) - (Q.ily >> l)) <= 1 && ((Q.ihz >> l) - (Q.ilz >> l)) <= 1) {
-                from_root = false;
-                const float edge = (float)(1 << l);
-                const int dxl = G.dims[l][0], dyl = G.dims[l][1], dzl = G.dims[l][2];
-                for (int z = Q.ilz >> l; z <= (Q.ihz >> l); ++z) {
-                    if (z < 0 || z >= dzl) continue;
-                    for (int y = Q.ily >> l; y <= (Q.ihy >> l); ++y) {
-                        if (y < 0 || y >= dyl) continue;
-                        for (int x = Q.ilx >> l; x <= (Q.ihx >> l); ++x) {
-                            if (x < 0 || x >= dxl) continue;
-                            if (l > 0 && G.mask[l][((int64_t)z * dyl + y) * dxl + x] == 0) continue;
-                            const float lb = box_lb(fx, fy, fz, x, y, z, edge);
-                            if (lb <= Q.bestc) stack[sp++] = pack_entry(lb, l, x, y, z);
+        const int nchain = chained ? (int)min((int64_t)WALK_CHAIN, a.nq - w * WALK_CHAIN) : 1;
+        int32_t warm = -1;
+        for (int j = 0; j < nchain; ++j) {
+            const int64_t gq = chained ? w * WALK_CHAIN + j : (int64_t)a.worklist[w];
+            if (!chained) warm = a.prev ? a.prev[gq] : -1;
+            bool bld = false;
+            int lc = 0, ext_slot = -1;
+            double thr2 = 0.0;
+            float gap = 0.f;
+            if (BUILD) {
+                bld = !a.cl.delta || a.cl.delta[(unsigned)gq / (unsigned)a.ns] <= a.cl.build_max_delta;
+                gap = bld ? a.cl.gap_cells : 0.f;
+            }
+            Query Q;
+            setup_query(a, gq, Q, gap, warm);
+            if (BUILD && bld) { ext_slot = a.cl.ext[gq]; thr2 = list_thr2(Q.best, a.cl.skin); }
+            const float fx = Q.fx, fy = Q.fy, fz = Q.fz;
+            unsigned long long stack[GRID_STACK];
+            int sp = 0;
+            const int top = G.nlevels - 1;
+            bool from_root = true;
+            if (Q.has_span) {
+                // lowest level whose <= 2 x 2 x 2 nodes cover the ball's bounding cube
+                int l = 0;
+                while (l < top && (((Q.ihx >> l) - (Q.ilx >> l)) > 1 || ((Q.ihy >> l) - (Q.ily >> l)) > 1 || ((Q.ihz >> l) - (Q.ilz >> l)) > 1)) ++l;
+                if (((Q.ihx >> l) - (Q.ilx >> l)) <= 1 && ((Q.ihy >> l) - (Q.ily >> l)) <= 1 && ((Q.ihz >> l) - (Q.ilz >> l)) <= 1) {
+                    from_root = false;
+                    const float edge = (float)(1 << l);
+                    const int dxl = G.dims[l][0], dyl = G.dims[l][1], dzl = G.dims[l][2];
+                    for (int z = Q.ilz >> l; z <= (Q.ihz >> l); ++z) {
+                        if (z < 0 || z >= dzl) continue;
+                        for (int y = Q.ily >> l; y <= (Q.ihy >> l); ++y) {
+                            if (y < 0 || y >= dyl) continue;
+                            for (int x = Q.ilx >> l; x <= (Q.ihx >> l); ++x) {
+                                if (x < 0 || x >= dxl) continue;
+                                if (l > 0 && G.mask[l][((int64_t)z * dyl + y) * dxl + x] == 0) continue;
+                                const float lb = box_lb(fx, fy, fz, x, y, z, edge);
+                                if (lb <= Q.bestc) stack[sp++] = pack_entry(lb, l, x, y, z);
+                            }
                         }
                     }
                 }
             }
-        }
-        if (from_root) stack[sp++] = pack_entry(0.f, top, 0, 0, 0);
+            if (from_root) stack[sp++] = pack_entry(0.f, top, 0, 0, 0);
 
-        while (true) {
-            int32_t s0 = 0, s1 = 0;
-            bool have_leaf = false;
-            // phase 1: pop / expand until a leaf cell is in hand
             while (sp > 0) {
                 const unsigned long long e = stack[--sp];
                 const float lbf = __uint_as_float((unsigned)(e >> 34) << 1);
@@ -339,17 +472,34 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
                 const int ix = (int)(lo32 & 1023u), iy = (int)((lo32 >> 10) & 1023u), iz = (int)((lo32 >> 20) & 1023u);
                 ++n_nodes;
                 if (level == 0) {
+                    // exact FP64 scan of the leaf's points
                     const int64_t c = ((int64_t)iz * G.dims[0][1] + iy) * G.dims[0][0] + ix;
-                    s0 = G.cell_start[c];
-                    s1 = G.cell_start[c + 1];
-                    have_leaf = true;
-                    break;
+                    const int32_t s0 = G.cell_start[c], s1 = G.cell_start[c + 1];
+                    ++n_cells;
+                    n_pts += (unsigned long long)(s1 - s0);
+                    bool improved = false;
+                    for (int32_t p = s0; p < s1; ++p) {
+                        const GridPoint gp = G.pts[p];
+                        const double d = dist2_exact(gp.x, gp.y, gp.z, Q.qx, Q.qy, Q.qz);
+                        if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
+                            Q.best = d; Q.bidx = gp.orig; improved = true;
+                            if (BUILD && bld) thr2 = list_thr2(Q.best, a.cl.skin);
+                        }
+                        if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p);
+                    }
+                    if (improved) Q.bestc = (BUILD && bld) ? best_ub_cells_gap(Q.best, G.inv_cell, a.cl.gap_cells) : best_ub_cells(Q.best, inv_cell2);
+                    continue;
                 }
                 const int64_t c = ((int64_t)iz * G.dims[level][1] + iy) * G.dims[level][0] + ix;
                 unsigned m = G.mask[level][c];
                 const float edge = (float)(1 << (level - 1));              // child edge in cells
-                const float cx = (float)(2 * ix + 1) * edge, cy = (float)(2 * iy + 1) * edge, cz = (float)(2 * iz + 1) * edge;
-                const unsigned oct = (fx >= cx ? 1u : 0u) | (fy >= cy ? 2u : 0u) | (fz >= cz ? 4u : 0u);
+                // per-axis squared bounds of the two half slabs; a child's bound is one pick per axis
+                const float bx = (float)(2 * ix) * edge, by = (float)(2 * iy) * edge, bz = (float)(2 * iz) * edge;
+                float ax0 = axis_lb(fx, bx, edge), ax1 = axis_lb(fx, bx + edge, edge);
+                float ay0 = axis_lb(fy, by, edge), ay1 = axis_lb(fy, by + edge, edge);
+                float az0 = axis_lb(fz, bz, edge), az1 = axis_lb(fz, bz + edge, edge);
+                ax0 *= ax0; ax1 *= ax1; ay0 *= ay0; ay1 *= ay1; az0 *= az0; az1 *= az1;
+                const unsigned oct = (fx >= bx + edge ? 1u : 0u) | (fy >= by + edge ? 2u : 0u) | (fz >= bz + edge ? 4u : 0u);
                 // permute the mask so that bit t <-> child (t ^ oct); then high bits = far octants
                 if (oct & 1u) m = ((m & 0xAAu) >> 1) | ((m & 0x55u) << 1);
                 if (oct & 2u) m = ((m & 0xCCu) >> 2) | ((m & 0x33u) << 2);
@@ -358,52 +508,62 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
                     const int t = 31 - __clz(m);                           // far first, so the near octant is popped first
                     m &= ~(1u << t);
                     const int k = t ^ (int)oct;
-                    const int x = 2 * ix + (k & 1), y = 2 * iy + ((k >> 1) & 1), z = 2 * iz + (k >> 2);
-                    const float lb = box_lb(fx, fy, fz, x, y, z, edge);
-                    if (lb <= Q.bestc && sp < GRID_STACK) stack[sp++] = pack_entry(lb, level - 1, x, y, z);
+                    const float lb = ((((k & 1) ? ax1 : ax0) + ((k & 2) ? ay1 : ay0)) + ((k & 4) ? az1 : az0)) * (1.f - 6e-7f);
+                    if (lb <= Q.bestc && sp < GRID_STACK)
+                        stack[sp++] = pack_entry(lb, level - 1, 2 * ix + (k & 1), 2 * iy + ((k >> 1) & 1), 2 * iz + (k >> 2));
                 }
             }
-            if (!have_leaf) break;
-            // phase 2: exact FP64 scan of the leaf's points
-            ++n_cells;
-            n_pts += (unsigned long long)(s1 - s0);
-            scan_points(G, s0, s1, Q, inv_cell2);
+            a.idx[gq] = Q.bidx;
+            if (a.d2) a.d2[gq] = Q.best;
+            if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, ext_slot);
+            else if (a.cl.cnt) a.cl.cnt[gq] = -1;
+            warm = Q.bidx;
         }
-        a.idx[gq] = Q.bidx;
-        if (a.d2) a.d2[gq] = Q.best;
-        if (a.lb2) a.lb2[gq] = 0.f;                          // the walk gives no exhaustive-radius guarantee
     }
     flush_counters(a.counters, n_pts, n_cells, n_nodes);
 }
 
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz, int64_t ns,
                     const double* d_T, int64_t nhyp, const int32_t* d_prev, int32_t* d_idx, double* d_d2,
-                    unsigned long long* d_counters, GridScratch& sc, float* d_lb2, const float* d_delta, cudaStream_t st) {
+                    unsigned long long* d_counters, GridScratch& sc, const CandView* cl, bool scan_lists, cudaStream_t st) {
     PCREG_REQUIRE(m->has_grid, "grid NN requested but the model was created without build_grid");
     GridArgs a{};
     a.g = m->grid; a.md = m->md.p;
     a.sx = d_sx; a.sy = d_sy; a.sz = d_sz; a.ns = ns; a.T = d_T; a.nq = nhyp * ns;
     a.prev = d_prev; a.idx = d_idx; a.d2 = d_d2; a.counters = d_counters;
-    a.lb2 = d_lb2; a.delta = d_delta;
-    a.gap_cells = d_lb2 ? 0.15f : 0.f;
+    if (cl) a.cl = *cl;
+    static const int row_span_env = [] { const char* e = getenv("PCREG_ROW_SPAN"); return e ? atoi(e) : 0; }();
+    a.row_span = row_span_env > 0 ? row_span_env : GRID_ROW_SPAN;
     PCREG_REQUIRE(a.nq > 0, "nn_grid: no queries");
     PCREG_REQUIRE(a.nq < 2147483647LL, "nn_grid: too many queries in one launch");
+    PCREG_REQUIRE(!cl || (int64_t)cl->cap * a.nq < ((int64_t)1 << 40), "nn_grid: candidate lists too large");
     const int64_t blocks = (a.nq + 127) / 128;
     const int walk_blocks = (int)std::min<int64_t>(blocks, (int64_t)ctx().sm_count * 64);
     if (d_prev) {
         if (sc.worklist.n < (size_t)a.nq) sc.worklist.alloc((size_t)a.nq);
-        if (sc.count.n < 1) sc.count.alloc(1);
-        a.worklist = sc.worklist.p; a.work_count = sc.count.p;
-        PCREG_CUDA(cudaMemsetAsync(sc.count.p, 0, sizeof(unsigned int), st));
+        if (sc.count.n < 2) sc.count.alloc(2);
+        PCREG_CUDA(cudaMemsetAsync(sc.count.p, 0, 2 * sizeof(unsigned int), st));
         const int direct_blocks = (int)std::min<int64_t>(blocks, (int64_t)ctx().sm_count * 16);
-        if (d_lb2) k_nn_grid_direct<true><<<direct_blocks, 128, 0, st>>>(a);
-        else       k_nn_grid_direct<false><<<direct_blocks, 128, 0, st>>>(a);
+        if (cl && scan_lists) {
+            if (sc.worklist0.n < (size_t)a.nq) sc.worklist0.alloc((size_t)a.nq);
+            a.worklist = sc.worklist0.p; a.work_count = sc.count.p + 1;
+            k_nn_list<<<(unsigned)blocks, 128, 0, st>>>(a);
+            PCREG_LAUNCHED();
+            a.in_list = sc.worklist0.p; a.in_count = sc.count.p + 1;
+        }
+        a.worklist = sc.worklist.p; a.work_count = sc.count.p;
+        if (cl) k_nn_grid_direct<true><<<direct_blocks, 128, 0, st>>>(a);
+        else    k_nn_grid_direct<false><<<direct_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
-        k_nn_grid_walk<<<walk_blocks, 128, 0, st>>>(a);
+        a.in_list = nullptr; a.in_count = nullptr;
+        if (cl) k_nn_grid_walk<true><<<walk_blocks, 128, 0, st>>>(a);
+        else    k_nn_grid_walk<false><<<walk_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
     } else {
         a.worklist = nullptr; a.work_count = nullptr;
-        k_nn_grid_walk<<<walk_blocks, 128, 0, st>>>(a);
+        const int64_t chains = (a.nq + WALK_CHAIN - 1) / WALK_CHAIN;
+        const int chain_blocks = (int)std::min<int64_t>((chains + 127) / 128, (int64_t)ctx().sm_count * 64);
+        k_nn_grid_walk<false><<<chain_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
     }
 }

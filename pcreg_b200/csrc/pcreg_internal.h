@@ -108,6 +108,24 @@ struct GridView {               // passed by value to kernels
     double inv_cell;
 };
 
+// Candidate ("Verlet") lists of the grid NN path, one per query of the current hypothesis chunk: every model
+// point within R_list = r0 + skin of the position q0 the query had when its list was built.  A later ICP pass
+// scans the list and accepts the result when (best list distance) + |q - q0| < R_list (nn_grid.cu).
+struct CandView {               // passed by value to kernels
+    float4* hdr;                // [nq] (q0 - grid origin) in FP32, w = R_list (rounded down)
+    int32_t* cnt;               // [nq] list length; -1 = no list.  nullptr: lists disabled
+    int32_t* list;              // [nq][cap] positions into GridView::pts
+    int32_t cap;
+    int32_t* ext;               // [nq] extension slot of the query (-1: none): entries cap.. of long lists
+    int32_t* ext_list;          // [ext_slots][ext_cap]
+    unsigned int* ext_count;    // slots handed out so far
+    int32_t ext_cap, ext_slots;
+    float gap_cells;            // a building search is exhaustive within (best distance + gap), in cell units
+    double skin;                // model units, <= gap_cells * cell: margin of the list around the best distance
+    const float* delta;         // [nhyp] or null: displacement bound of the last pose update (build only when small)
+    float build_max_delta;
+};
+
 }  // namespace pcreg
 
 struct pcreg_model {
@@ -149,13 +167,15 @@ void nn_brute_launch(const pcreg_model* m, const double* d_sx, const double* d_s
                      int32_t* d_idx, double* d_d2, NNScratch& scratch, cudaStream_t st);
 // Per-call scratch of the grid path: the work list handed from the direct kernel to the walk kernel.
 struct GridScratch {
-    DevBuf<int32_t> worklist;       // [nq]
-    DevBuf<unsigned int> count;     // [1]
+    DevBuf<int32_t> worklist;       // [nq] direct -> walk
+    DevBuf<int32_t> worklist0;      // [nq] list scan -> direct
+    DevBuf<unsigned int> count;     // [2]
 };
+// cl: candidate lists of this chunk or nullptr; scan_lists: lists may exist (a build pass has run)
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz,
                     int64_t ns, const double* d_T, int64_t nhyp, const int32_t* d_prev,
                     int32_t* d_idx, double* d_d2, unsigned long long* d_visit_counters, GridScratch& scratch,
-                    float* d_lb2 /*[nq] in/out or null*/, const float* d_delta /*[nhyp] or null*/, cudaStream_t st);
+                    const CandView* cl, bool scan_lists, cudaStream_t st);
 
 // Select / weight / 17 sums / Kabsch / compose, one block per hypothesis.
 struct IcpUpdateArgs {

@@ -163,3 +163,23 @@ def test_icp_larger_batch_properties(pcreg):
     R = a["T"][:, :3, :3]
     assert np.max(np.abs(R @ np.swapaxes(R, 1, 2) - np.eye(3))) < 1e-12
     m.destroy()
+
+
+def test_icp_candidate_lists_are_exact_and_used(pcreg):
+    """Grid NN answers most steady-state queries from per-query candidate lists (nn_grid.cu: k_nn_list).  A list
+    answer is only accepted when it is provably the exact nearest neighbour, so 30 iterations of grid ICP must
+    stay bit-identical to brute-force ICP (any differing correspondence would change the pose sums), and the
+    profile must show that the list path really ran."""
+    model = synth.make_model(150_000, 2024)
+    src, T_gt, c = synth.make_source(model, 2500, 0.3, 2025)
+    T0 = synth.pose_grid(T_gt, c, 4, (2, 2, 2), 8.0, 1.5, 9)
+    m = pcreg.Model(model, grid=True)
+    pcreg.set_profiling(True)
+    a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=30, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    prof = pcreg.last_profile()
+    pcreg.set_profiling(False)
+    b = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=30, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True)
+    assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["T"], b["T"])
+    assert np.array_equal(a["rmse_hist"], b["rmse_hist"])
+    assert prof["certified_queries"] > 0.3 * prof["nn_queries"], prof
+    m.destroy()
