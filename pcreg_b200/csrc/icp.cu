@@ -24,10 +24,10 @@
 
 namespace pcreg {
 
-constexpr int UPD_THREADS = 512;
+constexpr int UPD_THREADS = 256;
 
 // One block per hypothesis.
-__global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
+__global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
     __shared__ double Ts[16];
     __shared__ double red[KABSCH_NSUMS * 32];
     __shared__ long long redll[32];
@@ -85,29 +85,50 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_cons
     for (int k = 0; k < KABSCH_NSUMS; ++k) s[k] = 0.0;
     long long n_used = 0;
     const double px = a.pivot[0], py = a.pivot[1], pz = a.pivot[2];
-    for (int64_t i = tid; i < ns; i += UPD_THREADS) {
-        const int32_t j = idx[i];
-        if (j < 0) continue;
-        const double d = d2[i];
-        const bool keep = !reject || d < a.thDist2;
+    // Branch-free body, four correspondences per trip: the index / residual / source loads and the model gathers
+    // of a trip are independent, so they are all in flight together (the loop is bound by their latency).
+    // A zero weight contributes exact zeros to every sum.
+    auto weight_of = [&](int64_t i, int32_t j, double d) -> double {
+        const bool keep = j >= 0 && (!reject || d < a.thDist2);
         double w = 0.0;
         if (a.mode == PCREG_ICP_PLAIN) {
             w = keep ? 1.0 : 0.0;
         } else if (a.mode == PCREG_ICP_KNN) {
             const unsigned long long key = a.keys[h * ns + i];
-            w = key_selected(key, vK, all_eq) ? 1.0 : 0.0;
-        } else {
-            if (keep) {
-                const double r = __dsqrt_rn(d);
-                w = fmax(__dsub_rn(a.R_w, r), 0.0);
-            }
+            w = (j >= 0 && key_selected(key, vK, all_eq)) ? 1.0 : 0.0;
+        } else if (keep) {
+            w = fmax(__dsub_rn(a.R_w, __dsqrt_rn(d)), 0.0);
         }
         if (a.w_src) w = __dmul_rn(w, a.w_src[i]);
-        if (w > 0.0) ++n_used;
-        if (w != 0.0) {
+        return w;
+    };
+    constexpr int UB = 4;
+    for (int64_t i0 = tid; i0 < ns; i0 += (int64_t)UB * UPD_THREADS) {
+        int32_t jj[UB]; double dd[UB], xs[UB], ys[UB], zs[UB], ww[UB];
+        ModelPointD mm[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int64_t i = i0 + (int64_t)u * UPD_THREADS;
+            const bool ok = i < ns;
+            const int64_t ic = ok ? i : tid;                 // tid < ns is guaranteed inside the loop
+            jj[u] = ok ? idx[ic] : -1;
+            dd[u] = d2[ic];
+            xs[u] = a.sx[ic]; ys[u] = a.sy[ic]; zs[u] = a.sz[ic];
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) mm[u] = a.md[jj[u] >= 0 ? jj[u] : 0];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int64_t i = i0 + (int64_t)u * UPD_THREADS;
+            ww[u] = (i < ns) ? weight_of(i, jj[u], dd[u]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const double w = ww[u], d = dd[u];
+            if (w > 0.0) ++n_used;
             double qx, qy, qz;
-            quick_tf(Ts, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
-            const ModelPointD m = a.md[j];
+            quick_tf(Ts, xs[u], ys[u], zs[u], qx, qy, qz);
+            const ModelPointD m = mm[u];
             const double q0 = qx - px, q1 = qy - py, q2 = qz - pz;
             const double m0 = m.x - px, m1 = m.y - py, m2 = m.z - pz;
             const double wq0 = w * q0, wq1 = w * q1, wq2 = w * q2;
@@ -346,7 +367,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     // chunk the hypotheses so that the per-correspondence scratch stays bounded
     size_t free_b = 0, total_b = 0;
     PCREG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + 24 + 4 * 64 + 4 * 448 / 16 : 0));
+    const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + 28 + 4 * 64 + 4 * 448 / 16 : 0));
     const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)24 << 30, total_b / 6));
     int64_t hc = (int64_t)std::max<size_t>(1, budget / per_hyp);
     hc = std::min(hc, nhyp);
@@ -368,9 +389,10 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     static const bool lists_on = [] { const char* e = getenv("PCREG_LISTS"); return !(e && e[0] == '0'); }();
     static const double list_skin_cells = [] { const char* e = getenv("PCREG_LIST_SKIN"); return e ? atof(e) : 0.6; }();
     static const int list_cap = [] { const char* e = getenv("PCREG_LIST_CAP"); int v = e ? atoi(e) : 64; return std::max(4, (v + 3) & ~3); }();
-    const bool use_lists = (o.nn == PCREG_NN_GRID) && lists_on && o.iters >= 3;
+    const bool use_lists = (o.nn == PCREG_NN_GRID) && lists_on && o.iters >= 3 && m->n <= ((int64_t)1 << 24);
     DevBuf<float4> cl_hdr(use_lists ? (size_t)hc * ns : 0);
-    DevBuf<int32_t> cl_cnt(use_lists ? (size_t)hc * ns : 0), cl_list(use_lists ? (size_t)hc * ns * list_cap : 0);
+    DevBuf<int2> cl_cnt(use_lists ? (size_t)hc * ns : 0);
+    DevBuf<int32_t> cl_list(use_lists ? (size_t)hc * ns * list_cap : 0);
     DevBuf<float> delta(use_lists ? (size_t)nhyp : 0);
     const int ext_cap = 448;                                               // wide balls: up to list_cap + 448 candidates
     const int64_t ext_slots = use_lists ? std::max<int64_t>(1024, hc * ns / 16) : 0;
@@ -419,6 +441,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         cl.skin = (double)cl.gap_cells * m->grid.cell * (1.0 - 1e-6);
         static const double build_frac = [] { const char* e = getenv("PCREG_LIST_BUILD"); return e ? atof(e) : 1.0; }();
         cl.build_max_delta = (float)(build_frac * cl.skin);
+        cl.inv_level = (float)(255.0 / (2.0 * cl.skin));
         PCREG_CUDA(cudaMemsetAsync(delta.p, 0x7f, delta.bytes(), st));      // "large" until the first update writes it
     }
     double nn_launches = 0, upd_launches = 0;
@@ -427,7 +450,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         int32_t* cur = idxA.p; int32_t* prev = idxB.p;
         bool have_prev = false;
         if (use_lists) {
-            PCREG_CUDA(cudaMemsetAsync(cl_cnt.p, 0xff, (size_t)hn * ns * sizeof(int32_t), st));     // -1: no list yet
+            PCREG_CUDA(cudaMemsetAsync(cl_cnt.p, 0xff, (size_t)hn * ns * sizeof(int2), st));        // -1: no list yet
             PCREG_CUDA(cudaMemsetAsync(cl_ext.p, 0xff, (size_t)hn * ns * sizeof(int32_t), st));     // -1: no extension slot
             PCREG_CUDA(cudaMemsetAsync(cl_ext_count.p, 0, sizeof(unsigned int), st));
             cl.delta = delta.p + h0;

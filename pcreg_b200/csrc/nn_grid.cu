@@ -178,7 +178,12 @@ __device__ __forceinline__ void worklist_append(const GridArgs& a, bool defer, i
 
 // append grid position p to the list under construction: the first cl.cap entries live in the query's own
 // row, longer lists (wide balls) continue in an extension slot taken from a shared pool on first need
-__device__ __forceinline__ void list_append(const CandView& cl, int64_t gq, int& lc, int& ext_slot, int32_t p) {
+// entry = position << 8 | level, level = where sqrt(d2) falls in [lo, lo + 2 skin] on a 256-step scale, rounded DOWN by
+// a whole step (the scan skips an entry only if even the lower edge of its level is out of reach)
+__device__ __forceinline__ void list_append(const CandView& cl, int64_t gq, int& lc, int& ext_slot, int32_t pos, double d, float lo) {
+    const float sd = __fsqrt_rd(__double2float_rd(d));
+    const int level = min(max((int)floorf((sd - lo) * cl.inv_level) - 1, 0), 255);
+    const int32_t p = (int32_t)(((unsigned)pos << 8) | (unsigned)level);
     if (lc < cl.cap) {
         cl.list[gq * cl.cap + lc] = p;
     } else {
@@ -192,16 +197,16 @@ __device__ __forceinline__ void list_append(const CandView& cl, int64_t gq, int&
     ++lc;
 }
 // close the list of a finished search: header + count, or "no list"
-__device__ __forceinline__ void list_commit(const CandView& cl, const GridView& G, int64_t gq, const Query& Q, bool bld, int lc, int ext_slot) {
+__device__ __forceinline__ void list_commit(const CandView& cl, const GridView& G, int64_t gq, const Query& Q, bool bld, int lc, int ext_slot, float lo) {
     if (ext_slot >= 0) cl.ext[gq] = ext_slot;
     if (bld && lc > 0 && (lc <= cl.cap || (ext_slot >= 0 && lc <= cl.cap + cl.ext_cap))) {
         // every model point within R_list of this position is in the list
         const double rl = (sqrt(Q.best) + cl.skin) * (1.0 - 1e-7);
         cl.hdr[gq] = make_float4(__double2float_rn(Q.qx - G.origin[0]), __double2float_rn(Q.qy - G.origin[1]),
                                  __double2float_rn(Q.qz - G.origin[2]), __double2float_rd(rl));
-        cl.cnt[gq] = lc;
+        cl.cnt[gq] = make_int2(lc, __float_as_int(lo));
     } else {
-        cl.cnt[gq] = -1;
+        cl.cnt[gq] = make_int2(-1, 0);
     }
 }
 
@@ -230,6 +235,7 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
     bool bld = false;
     int lc = 0, ext_slot = -1;
     double thr2 = 0.0;
+    float lo = 0.f;
 
     while (true) {
         // ---- batched fetch ----
@@ -258,7 +264,10 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
                         const float t = axis_lb(Q.fz, (float)z, 1.f);
                         dz2 = t * t;
                         have = true;
-                        if (BUILD) { lc = 0; ext_slot = bld ? a.cl.ext[gq] : -1; thr2 = bld ? list_thr2(Q.best, a.cl.skin) : 0.0; }
+                        if (BUILD) {
+                            lc = 0; ext_slot = bld ? a.cl.ext[gq] : -1; thr2 = bld ? list_thr2(Q.best, a.cl.skin) : 0.0;
+                            lo = __fsqrt_rd(__double2float_rd(Q.best)) - (float)a.cl.skin;      // every listed point is within [.., lo + 2 skin]
+                        }
                     } else {
                         defer = true;
                     }
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
             if (z > z1) {                                    // rows exhausted: done with this query
                 a.idx[gq] = Q.bidx;
                 if (a.d2) a.d2[gq] = Q.best;
-                if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, ext_slot);
+                if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, ext_slot, lo);
                 have = false;
             } else {                                         // ROW step
                 float dy2 = axis_lb(Q.fy, (float)y, 1.f);
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
                     Q.bestc = best_ub_cells(Q.best, inv_cell2);
                 }
             }
-            if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p);
+            if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p, d, lo);
             ++p;
         }
     }
@@ -318,31 +327,41 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
 }
 
 // ---- kernel 0: candidate-list scan -------------------------------------------------------------------------
-// Latency-bound by construction (count -> list entries in HBM -> model points in L2), so the loads are software
-// pipelined: the first 8 entries are requested together with the count and the header, the next 8 while the
-// current 8 points are in flight.
+// Bound by the gather rate of the model points (one L1 wavefront per lane and candidate), so most gathers are
+// avoided: a candidate k was at distance d0_k from the build position q0, hence is at least d0_k - moved from the
+// moved query, while the build-time neighbour is at most r0 + moved away.  Only candidates with
+// d0_k <= r0 + 2 moved can win or tie; d0_k is stored on a 256-level scale in the low byte of the entry (rounded
+// down), so the test is one integer compare and the skipped entries cost 4 streamed bytes each.
 struct GP4 { double x, y, z; long long w; };     // one GridPoint as four 64-bit registers (orig in the low word of w)
-__device__ __forceinline__ GP4 ldg_point(const GridPoint* p) {
+__device__ __forceinline__ GP4 ldg_point(const GridPoint* p, bool use) {
     GP4 r;
-    // one 256-bit load; volatile so that the eight gathers of a batch are issued back to back
-    asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=l"(r.w) : "l"(p));
+    r.x = r.y = r.z = 1.0e300; r.w = 0x7fffffffll;       // an unused slot never wins
+    if (use) asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=l"(r.w) : "l"(p));
     return r;
 }
 struct ListScan {
+    const GridPoint* __restrict__ pts;
     double qx, qy, qz, best;
     int32_t bidx;
-    __device__ __forceinline__ void eval8(const GridPoint* __restrict__ pts, const int4& ea, const int4& eb, int n) {
-        // n = valid entries among the 8 (>= 1); invalid ones repeat entry 0 (harmless)
-        const int p0 = ea.x, p1 = n > 1 ? ea.y : p0, p2 = n > 2 ? ea.z : p0, p3 = n > 3 ? ea.w : p0;
-        const int p4 = n > 4 ? eb.x : p0, p5 = n > 5 ? eb.y : p0, p6 = n > 6 ? eb.z : p0, p7 = n > 7 ? eb.w : p0;
-        const GP4 g0 = ldg_point(pts + p0), g1 = ldg_point(pts + p1), g2 = ldg_point(pts + p2), g3 = ldg_point(pts + p3);
-        const GP4 g4 = ldg_point(pts + p4), g5 = ldg_point(pts + p5), g6 = ldg_point(pts + p6), g7 = ldg_point(pts + p7);
-        take(g0); take(g1); take(g2); take(g3); take(g4); take(g5); take(g6); take(g7);
-    }
+    int lmax;
     __device__ __forceinline__ void take(const GP4& g) {
         const double d = dist2_exact(g.x, g.y, g.z, qx, qy, qz);
         const int32_t orig = (int32_t)(g.w & 0xffffffffll);
         if (d < best || (d == best && orig < bidx)) { best = d; bidx = orig; }
+    }
+    __device__ __forceinline__ void scan(const int32_t* __restrict__ L, int n) {
+        const int4* __restrict__ L4 = reinterpret_cast<const int4*>(L);
+        int4 nx = L4[0];
+        for (int k = 0; k < n; k += 4) {
+            const int4 e = nx;
+            if (k + 4 < n) nx = L4[(k >> 2) + 1];
+            const int m = n - k;                             // valid entries among the 4 (>= 1)
+            const bool u0 = (e.x & 255) <= lmax, u1 = m > 1 && (e.y & 255) <= lmax, u2 = m > 2 && (e.z & 255) <= lmax,
+                       u3 = m > 3 && (e.w & 255) <= lmax;
+            const GP4 g0 = ldg_point(pts + ((unsigned)e.x >> 8), u0), g1 = ldg_point(pts + ((unsigned)e.y >> 8), u1);
+            const GP4 g2 = ldg_point(pts + ((unsigned)e.z >> 8), u2), g3 = ldg_point(pts + ((unsigned)e.w >> 8), u3);
+            if (u0) take(g0); if (u1) take(g1); if (u2) take(g2); if (u3) take(g3);
+        }
     }
 };
 
@@ -352,41 +371,32 @@ __global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArg
     const int64_t gq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool defer = false, done = false;
     if (gq < a.nq) {
-        const int4* __restrict__ L4 = reinterpret_cast<const int4*>(a.cl.list + gq * a.cl.cap);
-        const int cnt = a.cl.cnt[gq];
-        int4 na = L4[0], nb = L4[1];                  // requested before cnt is known (rows are allocated either way)
-        const float4 hd = a.cl.hdr[gq];
+        const int2 cs = a.cl.cnt[gq];
+        const int cnt = cs.x;
         if (cnt <= 0) {
             defer = true;
         } else {
+            const float4 hd = a.cl.hdr[gq];
             const unsigned h = (unsigned)gq / (unsigned)a.ns, i = (unsigned)gq - h * (unsigned)a.ns;
             ListScan S;
+            S.pts = G.pts;
             quick_tf(a.T + (size_t)h * 16, a.sx[i], a.sy[i], a.sz[i], S.qx, S.qy, S.qz);
             S.best = INFINITY; S.bidx = -1;
-            const int nbase = min(cnt, a.cl.cap);
-            for (int k = 0; k < nbase; k += 8) {
-                const int4 ea = na, eb = nb;
-                if (k + 8 < nbase) { na = L4[(k >> 2) + 2]; nb = L4[(k >> 2) + 3]; }
-                S.eval8(G.pts, ea, eb, nbase - k);
-            }
-            if (cnt > a.cl.cap) {
-                const int4* __restrict__ E4 = reinterpret_cast<const int4*>(a.cl.ext_list + (int64_t)a.cl.ext[gq] * a.cl.ext_cap);
-                const int next = cnt - a.cl.cap;
-                na = E4[0]; nb = E4[1];
-                for (int k = 0; k < next; k += 8) {
-                    const int4 ea = na, eb = nb;
-                    if (k + 8 < next) { na = E4[(k >> 2) + 2]; nb = E4[(k >> 2) + 3]; }
-                    S.eval8(G.pts, ea, eb, next - k);
-                }
-            }
             // upper bound of |q - q0| (q0 = position when the list was built; both rounded to FP32 here)
             const float fx = __double2float_rn(S.qx - G.origin[0]), fy = __double2float_rn(S.qy - G.origin[1]), fz = __double2float_rn(S.qz - G.origin[2]);
             const float ex = fx - hd.x, ey = fy - hd.y, ez = fz - hd.z;
             float moved = __fsqrt_ru(__fmaf_ru(ex, ex, __fmaf_ru(ey, ey, __fmul_ru(ez, ez))));
             moved = moved * (1.f + 1e-6f) + 3e-7f * (fabsf(fx) + fabsf(fy) + fabsf(fz) + fabsf(hd.x) + fabsf(hd.y) + fabsf(hd.z)) + 1e-30f;
+            const float skin = (float)a.cl.skin;
+            // r0 = R_list - skin (upper bound); levels whose lower edge lies beyond r0 + 2 moved cannot matter
+            const float reach = __fadd_ru(hd.w * (1.f + 1e-6f) - skin * (1.f - 1e-5f), 2.f * moved);
+            const float lv = (reach - __int_as_float(cs.y)) * a.cl.inv_level;
+            S.lmax = (lv >= 254.f) ? 255 : max((int)floorf(lv) + 1, 0);
+            S.scan(a.cl.list + gq * a.cl.cap, min(cnt, a.cl.cap));
+            if (cnt > a.cl.cap) S.scan(a.cl.ext_list + (int64_t)a.cl.ext[gq] * a.cl.ext_cap, cnt - a.cl.cap);
             // a model point outside the list is farther than R_list - moved from q: is the list's best closer?
             const float r1 = __fsqrt_ru(__double2float_ru(S.best));
-            if (__fadd_ru(r1, moved) * (1.f + 1e-6f) < hd.w) {
+            if (S.bidx >= 0 && __fadd_ru(r1, moved) * (1.f + 1e-6f) < hd.w) {
                 a.idx[gq] = S.bidx;
                 if (a.d2) a.d2[gq] = S.best;
                 done = true;
@@ -433,7 +443,11 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
             }
             Query Q;
             setup_query(a, gq, Q, gap, warm);
-            if (BUILD && bld) { ext_slot = a.cl.ext[gq]; thr2 = list_thr2(Q.best, a.cl.skin); }
+            float lo = 0.f;
+            if (BUILD && bld) {
+                ext_slot = a.cl.ext[gq]; thr2 = list_thr2(Q.best, a.cl.skin);
+                lo = __fsqrt_rd(__double2float_rd(Q.best)) - (float)a.cl.skin;
+            }
             const float fx = Q.fx, fy = Q.fy, fz = Q.fz;
             unsigned long long stack[GRID_STACK];
             int sp = 0;
@@ -485,7 +499,7 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
                             Q.best = d; Q.bidx = gp.orig; improved = true;
                             if (BUILD && bld) thr2 = list_thr2(Q.best, a.cl.skin);
                         }
-                        if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p);
+                        if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p, d, lo);
                     }
                     if (improved) Q.bestc = (BUILD && bld) ? best_ub_cells_gap(Q.best, G.inv_cell, a.cl.gap_cells) : best_ub_cells(Q.best, inv_cell2);
                     continue;
@@ -515,8 +529,8 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
             }
             a.idx[gq] = Q.bidx;
             if (a.d2) a.d2[gq] = Q.best;
-            if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, ext_slot);
-            else if (a.cl.cnt) a.cl.cnt[gq] = -1;
+            if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, ext_slot, lo);
+            else if (a.cl.cnt) a.cl.cnt[gq] = make_int2(-1, 0);
             warm = Q.bidx;
         }
     }
@@ -537,6 +551,7 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
     PCREG_REQUIRE(a.nq > 0, "nn_grid: no queries");
     PCREG_REQUIRE(a.nq < 2147483647LL, "nn_grid: too many queries in one launch");
     PCREG_REQUIRE(!cl || (int64_t)cl->cap * a.nq < ((int64_t)1 << 40), "nn_grid: candidate lists too large");
+    PCREG_REQUIRE(!cl || m->n <= ((int64_t)1 << 24), "nn_grid: candidate lists address at most 2^24 model points");
     const int64_t blocks = (a.nq + 127) / 128;
     const int walk_blocks = (int)std::min<int64_t>(blocks, (int64_t)ctx().sm_count * 64);
     if (d_prev) {

@@ -113,8 +113,9 @@ struct GridView {               // passed by value to kernels
 // scans the list and accepts the result when (best list distance) + |q - q0| < R_list (nn_grid.cu).
 struct CandView {               // passed by value to kernels
     float4* hdr;                // [nq] (q0 - grid origin) in FP32, w = R_list (rounded down)
-    int32_t* cnt;               // [nq] list length; -1 = no list.  nullptr: lists disabled
-    int32_t* list;              // [nq][cap] positions into GridView::pts
+    int2* cnt;                  // [nq] x = list length (-1 = no list), y = float bits of the level scale's lower end.  nullptr: disabled
+    int32_t* list;              // [nq][cap] (position into GridView::pts) << 8 | distance level at build time
+    float inv_level;            // 255 / (2 skin): levels per model unit
     int32_t cap;
     int32_t* ext;               // [nq] extension slot of the query (-1: none): entries cap.. of long lists
     int32_t* ext_list;          // [ext_slots][ext_cap]
