@@ -194,11 +194,15 @@ int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
  *   out[0] = NN kernel launches, out[1] = total NN kernel ms, out[2] = NN queries,
  *   out[3] = (query, model point) pairs evaluated by brute force,
  *   out[4] = update (select + 17-sum + Kabsch) kernel launches, out[5] = their total ms,
- *   out[6] = correspondences reduced, out[7] = grid points visited (exact count, grid NN),
- *   out[8] = grid cells visited.
- * Event timing is only collected when enabled (it serialises nothing but adds event records). */
+ *   out[6] = correspondences reduced;
+ *   grid NN, exact device-side counts: out[7] = model points / out[8] = cell rows visited by the row scan,
+ *   out[9] = pyramid nodes popped, out[10] = queries answered from their candidate list, out[11] = queries walked,
+ *   out[12] = queries row-scanned, out[13] = list entries read, out[14] = list points gathered,
+ *   out[15] = model points / out[16] = leaf cells visited by the walk;
+ *   out[17..19] = total ms and out[20..22] = launches of the list-scan / row-scan / walk kernels.
+ * Collected only when enabled: the counters add atomics to the kernels, so timed runs keep it off. */
 int  pcreg_set_profiling(int enabled);
-int  pcreg_last_profile(double out[16]);
+int  pcreg_last_profile(double out[32]);
 
 #ifdef __cplusplus
 }

@@ -346,12 +346,16 @@ def set_profiling(enabled: bool):
 
 
 def last_profile() -> dict:
-    buf = (C.c_double * 16)()
+    """Timing / device-side counts of the last ICP or NN call (include/pcreg.h: pcreg_last_profile)."""
+    buf = (C.c_double * 32)()
     L.check(L.lib().pcreg_last_profile(buf), "pcreg_last_profile")
     v = list(buf)
     return dict(nn_launches=v[0], nn_ms=v[1], nn_queries=v[2], brute_pairs=v[3], update_launches=v[4],
-                update_ms=v[5], correspondences=v[6], grid_points_visited=v[7], grid_cells_visited=v[8],
-                grid_nodes_popped=v[9], certified_queries=v[10], walked_queries=v[11], rowscan_queries=v[12])
+                update_ms=v[5], correspondences=v[6], grid_points_visited=v[7] + v[15], grid_cells_visited=v[8] + v[16],
+                grid_nodes_popped=v[9], certified_queries=v[10], walked_queries=v[11], rowscan_queries=v[12],
+                list_entries_read=v[13], list_points_gathered=v[14],
+                rowscan_points=v[7], rowscan_rows=v[8], walk_points=v[15], walk_leaves=v[16],
+                list_ms=v[17], rowscan_ms=v[18], walk_ms=v[19], list_launches=v[20], rowscan_launches=v[21], walk_launches=v[22])
 
 
 def launch_count() -> int:

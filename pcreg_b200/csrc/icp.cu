@@ -362,7 +362,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     if (o.nn == PCREG_NN_GRID) PCREG_REQUIRE(m->has_grid, "icp: grid NN requested but the model has no grid");
     Context& c = ctx();
     const bool prof = c.profiling;
-    for (int i = 0; i < 16; ++i) c.profile[i] = 0.0;
+    for (int i = 0; i < 32; ++i) c.profile[i] = 0.0;
 
     // chunk the hypotheses so that the per-correspondence scratch stays bounded
     size_t free_b = 0, total_b = 0;
@@ -381,7 +381,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     DevBuf<int32_t> frozen((size_t)nhyp);
     DevBuf<double> rmse_tmp(d_rmse ? 0 : (size_t)nhyp);
     DevBuf<int32_t> nused_tmp(d_n_used ? 0 : (size_t)nhyp);
-    DevBuf<unsigned long long> counters(8);
+    DevBuf<unsigned long long> counters(16);
     NNScratch scratch;
     GridScratch gscratch;
     // candidate lists (grid NN, nn_grid.cu): built by the full searches once a pose has nearly stopped moving,
@@ -407,10 +407,13 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     transpose16_launch(d_T0_cm, Twork.p, nhyp, st);
 
     std::vector<EventPair> evs;
+    std::vector<GridScratch::Mark> marks;
+    size_t ev_cursor = 0;
+    if (prof) { gscratch.timing = &marks; gscratch.ev_cursor = &ev_cursor; }
     auto ev_begin = [&](int kind) {
         if (!prof) return;
         EventPair e; e.kind = kind;
-        e.a = pooled_event(2 * evs.size()); e.b = pooled_event(2 * evs.size() + 1);
+        e.a = pooled_event(ev_cursor++); e.b = pooled_event(ev_cursor++);
         PCREG_CUDA(cudaEventRecord(e.a, st));
         evs.push_back(e);
     };
@@ -505,9 +508,17 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             (e.kind == 0 ? nn_ms : upd_ms) += ms;
             if (debug_times()) fprintf(stderr, "[pcreg] %s %.3f ms\n", e.kind == 0 ? "nn" : "update", ms);
         }
-        unsigned long long hcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long hcnt[16] = {0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
-        c.profile[10] = (double)hcnt[3]; c.profile[11] = (double)hcnt[4]; c.profile[12] = (double)hcnt[5];
+        for (int k = 3; k < 10; ++k) c.profile[7 + k] = (double)hcnt[k];       // out[10..16]
+        // per-kernel time of the grid path: the span from each mark to the next one of the same pass
+        for (size_t k = 0; k + 1 < marks.size(); ++k) {
+            if (marks[k].kind == 3) continue;
+            float ms = 0.f;
+            PCREG_CUDA(cudaEventElapsedTime(&ms, marks[k].ev, marks[k + 1].ev));
+            c.profile[17 + marks[k].kind] += ms;
+            c.profile[20 + marks[k].kind] += 1.0;
+        }
         const double nq = (double)nhyp * (double)ns * (double)(o.iters + 1);
         c.profile[0] = nn_launches; c.profile[1] = nn_ms; c.profile[2] = nq;
         c.profile[3] = (o.nn == PCREG_NN_BRUTE) ? nq * (double)m->n : 0.0;
@@ -592,12 +603,12 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
     PCREG_CUDA(cudaSetDevice(ctx().device));
     cudaStream_t st = 0;
     Context& c = ctx();
-    for (int i = 0; i < 16; ++i) c.profile[i] = 0.0;
+    for (int i = 0; i < 32; ++i) c.profile[i] = 0.0;
     std::vector<double> hq = to_double_cm(q, is_double, nq, ld);
     const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     DevBuf<double> d_q((size_t)nq * 3), d_T(16), d_d2((size_t)nq);
     DevBuf<int32_t> d_idx((size_t)nq);
-    DevBuf<unsigned long long> counters(8);
+    DevBuf<unsigned long long> counters(16);
     NNScratch scratch;
     GridScratch gscratch;
     PCREG_CUDA(cudaMemcpyAsync(d_q.p, hq.data(), d_q.bytes(), cudaMemcpyHostToDevice, st));
@@ -618,8 +629,9 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         float ms = 0.f;
         PCREG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         cudaEventDestroy(e0); cudaEventDestroy(e1);
-        unsigned long long hcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long hcnt[16] = {0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
+        for (int k = 3; k < 10; ++k) c.profile[7 + k] = (double)hcnt[k];
         c.profile[0] = 1; c.profile[1] = ms; c.profile[2] = (double)nq;
         c.profile[3] = nn_kind == PCREG_NN_BRUTE ? (double)nq * (double)m->n : 0.0;
         c.profile[7] = (double)hcnt[0]; c.profile[8] = (double)hcnt[1]; c.profile[9] = (double)hcnt[2];

@@ -387,9 +387,9 @@ int pcreg_shutdown(void) {
 }
 
 int pcreg_set_profiling(int enabled) { ctx().profiling = enabled != 0; return PCREG_OK; }
-int pcreg_last_profile(double out[16]) {
+int pcreg_last_profile(double out[32]) {
     if (!out) return PCREG_ERR_ARG;
-    for (int i = 0; i < 16; ++i) out[i] = ctx().profile[i];
+    for (int i = 0; i < 32; ++i) out[i] = ctx().profile[i];
     return PCREG_OK;
 }
 

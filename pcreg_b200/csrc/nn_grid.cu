@@ -46,9 +46,10 @@ struct GridArgs {
     int32_t* worklist;              // [nq] query ids handed to the next kernel (list -> direct -> walk)
     unsigned int* work_count;       // number of entries in worklist
     int row_span;                   // direct kernel: widest (y,z) cell span it row-scans itself
-    unsigned long long* counters;   // [0] points visited, [1] leaf cells / rows visited, [2] nodes popped,
-                                    // [3] queries answered from their candidate list, [4] queries walked,
-                                    // [5] queries row-scanned (may be null)
+    unsigned long long* counters;   // profiling only (may be null): [0] points / [1] rows visited by the row scan, [2] pyramid
+                                    // nodes popped, [3] queries answered from their list, [4] queries walked, [5] queries
+                                    // row-scanned, [6] list entries read, [7] list points gathered, [8] points / [9] leaf cells
+                                    // visited by the walk
 };
 
 constexpr int GRID_STACK = 80;
@@ -130,7 +131,7 @@ __device__ __forceinline__ void scan_points(const GridView& G, int32_t s0, int32
 }
 
 __device__ __forceinline__ void flush_counters(unsigned long long* counters, unsigned long long n_pts,
-                                               unsigned long long n_cells, unsigned long long n_nodes) {
+                                               unsigned long long n_cells, unsigned long long n_nodes, int i_pts = 0, int i_cells = 1) {
     if (!counters) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -139,8 +140,8 @@ __device__ __forceinline__ void flush_counters(unsigned long long* counters, uns
         n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (n_pts) atomicAdd(&counters[0], n_pts);
-        if (n_cells) atomicAdd(&counters[1], n_cells);
+        if (n_pts) atomicAdd(&counters[i_pts], n_pts);
+        if (n_cells) atomicAdd(&counters[i_cells], n_cells);
         if (n_nodes) atomicAdd(&counters[2], n_nodes);
     }
 }
@@ -217,7 +218,10 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t total = a.in_list ? (int64_t)*a.in_count : a.nq;
-    if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters[5], (unsigned long long)total);
+    if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&a.counters[5], (unsigned long long)total);
+        if (a.in_list) atomicAdd(&a.counters[3], (unsigned long long)(a.nq - total));      // the list scan answered the rest
+    }
     const int64_t per_warp = (total + nwarps - 1) / nwarps;
     int64_t next = warp_id * per_warp;                       // warp-uniform cursor into this warp's range
     const int64_t end = min(total, next + per_warp);
@@ -344,6 +348,7 @@ struct ListScan {
     double qx, qy, qz, best;
     int32_t bidx;
     int lmax;
+    unsigned n_read, n_gather;
     __device__ __forceinline__ void take(const GP4& g) {
         const double d = dist2_exact(g.x, g.y, g.z, qx, qy, qz);
         const int32_t orig = (int32_t)(g.w & 0xffffffffll);
@@ -361,6 +366,8 @@ struct ListScan {
             const GP4 g0 = ldg_point(pts + ((unsigned)e.x >> 8), u0), g1 = ldg_point(pts + ((unsigned)e.y >> 8), u1);
             const GP4 g2 = ldg_point(pts + ((unsigned)e.z >> 8), u2), g3 = ldg_point(pts + ((unsigned)e.w >> 8), u3);
             if (u0) take(g0); if (u1) take(g1); if (u2) take(g2); if (u3) take(g3);
+            n_read += (unsigned)min(m, 4);
+            n_gather += (unsigned)u0 + (unsigned)u1 + (unsigned)u2 + (unsigned)u3;
         }
     }
 };
@@ -369,7 +376,8 @@ __global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArg
     const GridView& G = a.g;
     const int lane = threadIdx.x & 31;
     const int64_t gq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool defer = false, done = false;
+    bool defer = false;
+    unsigned n_read = 0, n_gather = 0;
     if (gq < a.nq) {
         const int2 cs = a.cl.cnt[gq];
         const int cnt = cs.x;
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArg
             ListScan S;
             S.pts = G.pts;
             quick_tf(a.T + (size_t)h * 16, a.sx[i], a.sy[i], a.sz[i], S.qx, S.qy, S.qz);
-            S.best = INFINITY; S.bidx = -1;
+            S.best = INFINITY; S.bidx = -1; S.n_read = 0; S.n_gather = 0;
             // upper bound of |q - q0| (q0 = position when the list was built; both rounded to FP32 here)
             const float fx = __double2float_rn(S.qx - G.origin[0]), fy = __double2float_rn(S.qy - G.origin[1]), fz = __double2float_rn(S.qz - G.origin[2]);
             const float ex = fx - hd.x, ey = fy - hd.y, ez = fz - hd.z;
@@ -399,17 +407,14 @@ __global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArg
             if (S.bidx >= 0 && __fadd_ru(r1, moved) * (1.f + 1e-6f) < hd.w) {
                 a.idx[gq] = S.bidx;
                 if (a.d2) a.d2[gq] = S.best;
-                done = true;
             } else {
                 defer = true;
             }
+            n_read = S.n_read; n_gather = S.n_gather;
         }
     }
     worklist_append(a, defer, gq, lane);
-    if (a.counters) {
-        const unsigned dm = __ballot_sync(0xffffffffu, done);
-        if (lane == 0 && dm) atomicAdd(&a.counters[3], (unsigned long long)__popc(dm));
-    }
+    if (a.counters) flush_counters(a.counters, n_read, n_gather, 0, 6, 7);
 }
 
 // ---- kernel 2: pyramid walk --------------------------------------------------------------------------------
@@ -534,7 +539,7 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
             warm = Q.bidx;
         }
     }
-    flush_counters(a.counters, n_pts, n_cells, n_nodes);
+    flush_counters(a.counters, n_pts, n_cells, n_nodes, 8, 9);
 }
 
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz, int64_t ns,
@@ -552,6 +557,12 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
     PCREG_REQUIRE(a.nq < 2147483647LL, "nn_grid: too many queries in one launch");
     PCREG_REQUIRE(!cl || (int64_t)cl->cap * a.nq < ((int64_t)1 << 40), "nn_grid: candidate lists too large");
     PCREG_REQUIRE(!cl || m->n <= ((int64_t)1 << 24), "nn_grid: candidate lists address at most 2^24 model points");
+    auto mark = [&](int kind) {
+        if (!sc.timing) return;
+        cudaEvent_t ev = pooled_event((*sc.ev_cursor)++);
+        PCREG_CUDA(cudaEventRecord(ev, st));
+        sc.timing->push_back(GridScratch::Mark{kind, ev});
+    };
     const int64_t blocks = (a.nq + 127) / 128;
     const int walk_blocks = (int)std::min<int64_t>(blocks, (int64_t)ctx().sm_count * 64);
     if (d_prev) {
@@ -562,24 +573,30 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
         if (cl && scan_lists) {
             if (sc.worklist0.n < (size_t)a.nq) sc.worklist0.alloc((size_t)a.nq);
             a.worklist = sc.worklist0.p; a.work_count = sc.count.p + 1;
+            mark(0);
             k_nn_list<<<(unsigned)blocks, 128, 0, st>>>(a);
             PCREG_LAUNCHED();
             a.in_list = sc.worklist0.p; a.in_count = sc.count.p + 1;
         }
         a.worklist = sc.worklist.p; a.work_count = sc.count.p;
+        mark(1);
         if (cl) k_nn_grid_direct<true><<<direct_blocks, 128, 0, st>>>(a);
         else    k_nn_grid_direct<false><<<direct_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
         a.in_list = nullptr; a.in_count = nullptr;
+        mark(2);
         if (cl) k_nn_grid_walk<true><<<walk_blocks, 128, 0, st>>>(a);
         else    k_nn_grid_walk<false><<<walk_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
+        mark(3);
     } else {
         a.worklist = nullptr; a.work_count = nullptr;
         const int64_t chains = (a.nq + WALK_CHAIN - 1) / WALK_CHAIN;
         const int chain_blocks = (int)std::min<int64_t>((chains + 127) / 128, (int64_t)ctx().sm_count * 64);
+        mark(2);
         k_nn_grid_walk<false><<<chain_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
+        mark(3);
     }
 }
 

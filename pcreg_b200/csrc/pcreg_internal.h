@@ -54,7 +54,7 @@ struct Context {
     int  sm_count = 148;
     size_t smem_optin = 0;
     bool profiling = false;
-    double profile[16] = {0};
+    double profile[32] = {0};
     std::vector<cudaEvent_t> events;     // reusable timing events (profiling mode)
 };
 cudaEvent_t pooled_event(size_t i);      // i-th reusable event, created on first use
@@ -171,6 +171,11 @@ struct GridScratch {
     DevBuf<int32_t> worklist;       // [nq] direct -> walk
     DevBuf<int32_t> worklist0;      // [nq] list scan -> direct
     DevBuf<unsigned int> count;     // [2]
+    // profiling: event marks between the kernels of a pass (kind 0 = list scan starts, 1 = row scan starts,
+    // 2 = walk starts, 3 = pass ends); events are drawn from the pool through the caller's cursor
+    struct Mark { int kind; cudaEvent_t ev; };
+    std::vector<Mark>* timing = nullptr;
+    size_t* ev_cursor = nullptr;
 };
 // cl: candidate lists of this chunk or nullptr; scan_lists: lists may exist (a build pass has run)
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz,
