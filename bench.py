@@ -44,14 +44,19 @@ WORKLOADS = {
 }
 
 
-def make_inputs(w, rank):
+def make_inputs(w, rank, world=1):
+    """Synthetic inputs of workload w for one rank.  Multi-GPU (weak scaling): ONE pose grid of hyp * world poses --
+    the same rotations, the z lattice refined `world` times over the same extent -- dealt to the ranks round-robin,
+    so that every GPU gets a statistically identical share."""
     from pcreg_b200 import synth
     model = synth.make_model(w["nm"], w["seed"])
     src, T_gt, c = synth.make_source(model, w["ns"], w["sigma"], w["seed"])
     if w["hyp"] == 1:
         T0 = synth.perturb_pose(T_gt, c, synth.rot_axis_angle([0.3, -0.5, 0.8], np.deg2rad(5.0)), np.array([1.2, -1.0, 1.2]))[None]
     else:
-        T0 = synth.pose_grid(T_gt, c, w["rot"], w["trans"], w["max_deg"], 2.0, w["seed"] + 17 * rank)[: w["hyp"]]
+        nx, ny, nz = w["trans"]
+        T0 = synth.pose_grid(T_gt, c, w["rot"], (nx, ny, nz * world), w["max_deg"], (2.0, 2.0, 2.0 / world), w["seed"])
+        T0 = np.ascontiguousarray(T0[rank::world][: w["hyp"]])
     g = synth.rng(w["seed"] + 5)
     w_src = g.uniform(0.5, 1.0, w["ns"]) if w["mode"] == "weighted" else None
     return model, src, T0, w_src, T_gt
@@ -185,7 +190,7 @@ def gpu_workload(P, torch, w, rank, steps, warmup, dist=None, world=1, e2e_steps
     """Returns a dict of measurements for one workload on this rank (collectives included when world > 1)."""
     from pcreg_b200 import sharded, torch_ops
     dev = torch.device("cuda", torch.cuda.current_device())
-    model_h, src, T0, w_src, T_gt = make_inputs(w, rank)
+    model_h, src, T0, w_src, T_gt = make_inputs(w, rank, world)
     m = P.Model(model_h, grid=(w["nn"] == "grid"), cells_per_point=float(os.environ.get("PCREG_GRID_CPP", "0")))
     mode = dict(plain=P.ICP_PLAIN, knn=P.ICP_KNN, weighted=P.ICP_WEIGHTED)[w["mode"]]
     nn = P.NN_GRID if w["nn"] == "grid" else P.NN_BRUTE

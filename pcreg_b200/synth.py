@@ -95,15 +95,17 @@ def perturb_pose(T_gt, centre, R_p, t_p):
 
 def pose_grid(T_gt, centre, n_rot, n_trans_xyz, max_deg, pitch, seed):
     """slideMatchingWindow / completeExperiment style multi-start grid: n_rot random rotations (angle <=
-    max_deg about random axes through the patch centre) x a translation lattice (nx, ny, nz) of `pitch` mm."""
+    max_deg about random axes through the patch centre) x a translation lattice (nx, ny, nz) of `pitch` mm
+    (a scalar, or one pitch per axis)."""
     g = rng(seed)
     rots = [np.eye(3)]
     for _ in range(n_rot - 1):
         rots.append(rot_axis_angle(g.standard_normal(3), np.deg2rad(g.uniform(0, max_deg))))
     nx, ny, nz = n_trans_xyz
-    gx = (np.arange(nx) - (nx - 1) / 2) * pitch
-    gy = (np.arange(ny) - (ny - 1) / 2) * pitch
-    gz = (np.arange(nz) - (nz - 1) / 2) * pitch
+    px, py, pz = np.broadcast_to(np.asarray(pitch, dtype=np.float64), (3,))
+    gx = (np.arange(nx) - (nx - 1) / 2) * px
+    gy = (np.arange(ny) - (ny - 1) / 2) * py
+    gz = (np.arange(nz) - (nz - 1) / 2) * pz
     out = []
     for R in rots:
         for x in gx:
