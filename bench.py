@@ -190,7 +190,10 @@ def gpu_workload(P, torch, w, rank, steps, warmup, dist=None, world=1, e2e_steps
     """Returns a dict of measurements for one workload on this rank (collectives included when world > 1)."""
     from pcreg_b200 import sharded, torch_ops
     dev = torch.device("cuda", torch.cuda.current_device())
-    model_h, src, T0, w_src, T_gt = make_inputs(w, rank, world)
+    # PCREG_BENCH_SHARD="r/n": measure on ONE GPU the share that rank r of an n-GPU run would get (work-balance check)
+    shard = os.environ.get("PCREG_BENCH_SHARD")
+    in_rank, in_world = (int(shard.split("/")[0]), int(shard.split("/")[1])) if shard else (rank, world)
+    model_h, src, T0, w_src, T_gt = make_inputs(w, in_rank, in_world)
     m = P.Model(model_h, grid=(w["nn"] == "grid"), cells_per_point=float(os.environ.get("PCREG_GRID_CPP", "0")))
     mode = dict(plain=P.ICP_PLAIN, knn=P.ICP_KNN, weighted=P.ICP_WEIGHTED)[w["mode"]]
     nn = P.NN_GRID if w["nn"] == "grid" else P.NN_BRUTE

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpcreg_b200.so")
+# PCREG_LIB: load another build of the same library (A/B timing of kernel variants inside one GPU session)
+LIB_PATH = os.environ.get("PCREG_LIB") or os.path.join(HERE, "libpcreg_b200.so")
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
