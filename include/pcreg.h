@@ -87,6 +87,26 @@ int  pcreg_local_points_fill(const pcreg_model* m, const double* centres, int64_
                              const int64_t* offsets, const int32_t* status, double* pts_rel, int64_t ld_out,
                              double* dists, int32_t* orig_idx);
 
+/* ---- getSpacialHistogramDescriptors.m:2-183 (+ histcn.m:97-131), batched over keypoints --------- */
+typedef struct {
+    int64_t min_pts, max_pts;   /* options.min_pts / max_pts (getLocalPoints.m:31-34); max_pts < 0 = inf        */
+    double  R;                  /* options.R: neighbourhood radius (3.5 in GetSphericalDescriptors.m:133-139)    */
+    double  thVar[2];           /* options.thVar: eigenvalue-ratio rejection (:117-120); [1,1] = off             */
+    double  k_frac;             /* options.k: fraction of the points nearest to the centroid used for the PCA
+                                   (:76-84); <= 0 or 1 = 'all'                                                  */
+    int     align_points;       /* options.ALIGN_POINTS: rotate into the disambiguated PCA frame (:128-144)      */
+} pcreg_desc_opts;
+void pcreg_desc_opts_default(pcreg_desc_opts* o);
+/* keypoints: nkey x 3 column-major doubles (ld).  Bin edges as the reference builds them (:155-158): r_edges
+ * [nr+1] = nthroot(0:R^3/nr:R^3, 3), theta_edges [nt+1] = 0:pi/nt:pi, phi_edges [np+1] = -pi:2*pi/np:pi.
+ * desc: [nkey][nr*nt*np] doubles, descriptor k contiguous, element order reshape(counts, [], 1) of the
+ * nr x nt x np histogram (:164); rows of rejected keypoints are NaN.  status[k]: 0 = valid, 1 = getLocalPoints
+ * returned [] (:50-53), 2 = variance rejection (:117-120).  The reference returns only the valid rows, in keypoint
+ * order (:176-179) -- the host mirror compacts.  counts (optional): points inside each keypoint's sphere. */
+int  pcreg_spatial_histogram(const pcreg_model* m, const double* keypoints, int64_t nkey, int64_t ld,
+                             const pcreg_desc_opts* opts, const double* r_edges, int nr, const double* theta_edges, int nt,
+                             const double* phi_edges, int np, double* desc, int32_t* status, int64_t* counts);
+
 /* ---- AlignPoints family (AlignPoints.m:1-29, AlignPoints_KNN.m:1-60, AlignPoints_knn.m:1-43,
  *      AlignPoints_weighted.m:1-49, AlignPoints_c.m:1-44, AlignPoints_KNN_c.m:1-57), batched over
  *      neighbourhoods ---------------------------------------------------------------------------- */

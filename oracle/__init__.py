@@ -11,7 +11,7 @@ Parity status (see DESIGN.md section "Oracle"):
   * estimateTransform / quickTF / invertTF: PINNED by the reference's one
     self-contained known-answer vector (testTransformEstimation.m:2-14) and the
     analytic identities of testRANSAC.m:27-29,40-42 (tests/golden/kat_*.json).
-  * AlignPoints* family, ransac, getLocalPoints: restated line by line from the
+  * AlignPoints* family, ransac, getLocalPoints, getSpacialHistogramDescriptors (+ histcn): restated line by line from the
     .m files; MATLAB built-ins (pca/eig/sort/rank/round) restated from their
     documentation.  MATLAB/Octave are not installed here, so these are
     "parity unpinned" beyond algebraic identities.
@@ -27,5 +27,6 @@ from .align import (  # noqa: F401
     pca_eig, AlignPoints, AlignPoints_KNN, AlignPoints_knn, AlignPoints_weighted,
     AlignPoints_c, AlignPoints_KNN_c,
 )
+from .descriptors import getSpacialHistogramDescriptors, spatial_histogram_of, histogram_edges, histcn3, histcounts_bin  # noqa: F401
 from .nn import nn_brute, nn_kdtree  # noqa: F401
 from .icp import icp_single, icp_batch, ICP_PLAIN, ICP_KNN, ICP_WEIGHTED  # noqa: F401

@@ -5,7 +5,7 @@ this package is only the host-side mirror of the reference's MATLAB interface.  
 """
 from ._lib import PcregError, init, load, LIB_PATH  # noqa: F401
 from .api import (  # noqa: F401
-    Model, getLocalPoints, getLocalPoints_batch, AlignPoints, AlignPoints_KNN, AlignPoints_knn, AlignPoints_weighted, AlignPoints_c,
+    Model, getLocalPoints, getLocalPoints_batch, getSpacialHistogramDescriptors, spatial_histogram_edges, AlignPoints, AlignPoints_KNN, AlignPoints_knn, AlignPoints_weighted, AlignPoints_c,
     AlignPoints_KNN_c, align_points_batch, estimateTransform, estimate_transform_batch, ransac, ransac_seeded,
     icp_batch, icp_opts, set_profiling, last_profile, launch_count,
     NN_BRUTE, NN_GRID, ICP_PLAIN, ICP_KNN, ICP_WEIGHTED,

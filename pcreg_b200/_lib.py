@@ -31,6 +31,11 @@ class AlignOpts(C.Structure):
                 ("min_local", C.c_int64), ("C1", C.c_int), ("C2", C.c_int)]
 
 
+class DescOpts(C.Structure):
+    _fields_ = [("min_pts", C.c_int64), ("max_pts", C.c_int64), ("R", C.c_double), ("thVar", C.c_double * 2),
+                ("k_frac", C.c_double), ("align_points", C.c_int)]
+
+
 class RansacOpts(C.Structure):
     _fields_ = [("thDist", C.c_double), ("thInlrRatio", C.c_double), ("refine", C.c_int), ("reflection_fix", C.c_int)]
 
@@ -55,6 +60,9 @@ SIGNATURES = {
     "pcreg_local_points_count": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, c_i64p, c_i32p]),
     "pcreg_local_points_fill": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.c_double, c_i64p, c_i32p, c_f64p, C.c_int64,
                                           c_f64p, c_i32p]),
+    "pcreg_desc_opts_default": (None, [C.POINTER(DescOpts)]),
+    "pcreg_spatial_histogram": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.POINTER(DescOpts), c_f64p, C.c_int, c_f64p, C.c_int,
+                                          c_f64p, C.c_int, c_f64p, c_i32p, c_i64p]),
     "pcreg_align_opts_default": (None, [C.POINTER(AlignOpts)]),
     "pcreg_align_points": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, c_i64p, C.c_int64, C.POINTER(AlignOpts),
                                      C.c_void_p, c_f64p, c_f64p, c_i32p]),

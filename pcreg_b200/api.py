@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import AlignOpts, IcpOpts, ModelOpts, PcregError, RansacOpts  # noqa: F401
+from ._lib import AlignOpts, DescOpts, IcpOpts, ModelOpts, PcregError, RansacOpts  # noqa: F401
 
 NN_BRUTE, NN_GRID = 0, 1
 ICP_PLAIN, ICP_KNN, ICP_WEIGHTED = 0, 1, 2
@@ -141,6 +141,55 @@ def getLocalPoints(pts, R, c, min_points, max_points):
     m = Model(pts) if own else pts
     try:
         return getLocalPoints_batch(m, np.asarray(c, dtype=np.float64).reshape(1, 3), R, min_points, max_points)[0]
+    finally:
+        if own:
+            m.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# getSpacialHistogramDescriptors
+# ------------------------------------------------------------------------------------------------
+def spatial_histogram_edges(R, num_r=10, num_theta=7, num_phi=14):
+    """The bin edges exactly as getSpacialHistogramDescriptors.m:155-158 writes them (host arithmetic)."""
+    r_bins = np.cbrt(np.arange(num_r + 1) * (float(R) ** 3 / num_r))            # nthroot(0:R^3/NUM_R:R^3, 3)
+    phi_bins = -np.pi + np.arange(num_phi + 1) * (2 * np.pi / num_phi)          # -pi:2*pi/NUM_PHI:pi
+    theta_bins = np.arange(num_theta + 1) * (np.pi / num_theta)                 # 0:pi/NUM_THETA:pi
+    return r_bins, theta_bins, phi_bins
+
+
+def getSpacialHistogramDescriptors(pts, sample_pts, options, return_status=False):
+    """getSpacialHistogramDescriptors.m:2-183 -> (feat, desc): the keypoints that survive the getLocalPoints count
+    limits and the eigenvalue-ratio rejection, and their 980-bin spherical histograms (one row each).  `pts` is the
+    N x 3 cloud (uploaded for the call, as the reference signature has it) or a resident Model; `options` is the
+    reference's struct as a dict: min_pts, max_pts, R, thVar, k ('all' or a fraction), ALIGN_POINTS."""
+    own = not isinstance(pts, Model)
+    m = Model(pts) if own else pts
+    try:
+        kp = np.asfortranarray(np.asarray(sample_pts, dtype=np.float64).reshape(-1, 3))
+        nk = kp.shape[0]
+        o = DescOpts()
+        L.lib().pcreg_desc_opts_default(C.byref(o))
+        o.min_pts = int(options["min_pts"])
+        mp = options.get("max_pts", np.inf)
+        o.max_pts = -1 if mp is None or np.isinf(mp) else int(mp)
+        o.R = float(options["R"])
+        th = options.get("thVar", (1.0, 1.0))
+        o.thVar[0], o.thVar[1] = float(th[0]), float(th[1])
+        k = options.get("k", "all")
+        o.k_frac = 0.0 if isinstance(k, str) else float(k)
+        o.align_points = int(bool(options.get("ALIGN_POINTS", True)))
+        er, et, ep = (np.ascontiguousarray(e, dtype=np.float64) for e in spatial_histogram_edges(o.R))
+        nb = (len(er) - 1) * (len(et) - 1) * (len(ep) - 1)
+        desc = np.empty((nk, nb), dtype=np.float64)
+        status = np.empty(nk, dtype=np.int32)
+        counts = np.empty(nk, dtype=np.int64)
+        L.check(L.lib().pcreg_spatial_histogram(m.handle, _ptr(kp, L.c_f64p), nk, nk, C.byref(o), _ptr(er, L.c_f64p), len(er) - 1,
+                                                _ptr(et, L.c_f64p), len(et) - 1, _ptr(ep, L.c_f64p), len(ep) - 1,
+                                                _ptr(desc, L.c_f64p), _ptr(status, L.c_i32p), _ptr(counts, L.c_i64p)),
+                "pcreg_spatial_histogram")
+        ok = status == 0
+        out = (np.ascontiguousarray(kp[ok]), desc[ok])                           # :176-179: valid rows, keypoint order
+        return out + (status, counts) if return_status else out
     finally:
         if own:
             m.destroy()

@@ -140,6 +140,52 @@ static void local_points_run(const pcreg_model* m, const double* centres, int64_
     PCREG_CUDA(cudaStreamSynchronize(st));
 }
 
+// Device-resident variant for the descriptor pipeline (descriptor.cu): count -> host prefix sum over the accepted
+// centres -> fill; the neighbourhood points never leave the GPU.
+void local_points_device(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, double R, int64_t min_points,
+                         int64_t max_points, LocalPointsDev& out, cudaStream_t st) {
+    PCREG_REQUIRE(m && centres && nc >= 1 && ld >= nc && R > 0.0, "local_points: bad arguments");
+    const int nchunks = (int)((m->n + LP_CHUNK - 1) / LP_CHUNK);
+    const int64_t ntiles = (nc + LP_TILE - 1) / LP_TILE;
+    PCREG_REQUIRE(ntiles <= 65535, "local_points: at most 2,097,120 centres per call");
+    DevBuf<double> dc((size_t)nc * 3);
+    for (int a = 0; a < 3; ++a) PCREG_CUDA(cudaMemcpyAsync(dc.p + a * nc, centres + a * ld, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+    DevBuf<int32_t> cnt((size_t)ntiles * LP_TILE * nchunks);
+    DevBuf<int64_t> totals((size_t)nc);
+    LocalArgs a{};
+    a.md = m->md.p; a.n = m->n; a.cx = dc.p; a.cy = dc.p + nc; a.cz = dc.p + 2 * nc; a.nc = nc; a.R = R;
+    a.chunk_cnt = cnt.p; a.nchunks = nchunks;
+    dim3 grid((unsigned)nchunks, (unsigned)ntiles);
+    k_local_points<false><<<grid, 32, 0, st>>>(a);
+    PCREG_LAUNCHED();
+    k_local_scan<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(cnt.p, nchunks, nc, nullptr, nullptr, nullptr, totals.p);
+    PCREG_LAUNCHED();
+    out.counts.assign((size_t)nc, 0);
+    PCREG_CUDA(cudaMemcpyAsync(out.counts.data(), totals.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));
+    out.status.assign((size_t)nc, 0);
+    out.offsets.assign((size_t)nc + 1, 0);
+    for (int64_t k = 0; k < nc; ++k) {
+        const int64_t c = out.counts[k];
+        out.status[k] = (c < min_points || (max_points >= 0 && c > max_points)) ? 1 : 0;          // getLocalPoints.m:31-34
+        out.offsets[k + 1] = out.offsets[k] + (out.status[k] ? 0 : c);
+    }
+    out.ntotal = out.offsets[nc];
+    out.nel = std::max<int64_t>(out.ntotal, 1);
+    out.pts.alloc((size_t)out.nel * 3);
+    out.d_offsets.alloc((size_t)nc + 1);
+    DevBuf<int64_t> base((size_t)nc * nchunks);
+    DevBuf<int32_t> d_st((size_t)nc);
+    PCREG_CUDA(cudaMemcpyAsync(out.d_offsets.p, out.offsets.data(), ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
+    PCREG_CUDA(cudaMemcpyAsync(d_st.p, out.status.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    k_local_scan<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(cnt.p, nchunks, nc, out.d_offsets.p, d_st.p, base.p, nullptr);
+    PCREG_LAUNCHED();
+    a.chunk_base = base.p; a.out = out.pts.p; a.ld_out = out.nel; a.dists = nullptr; a.orig = nullptr;
+    k_local_points<true><<<grid, 32, 0, st>>>(a);
+    PCREG_LAUNCHED();
+    PCREG_CUDA(cudaStreamSynchronize(st));          // the per-call scratch above is released on return
+}
+
 }  // namespace pcreg
 
 using namespace pcreg;

@@ -204,6 +204,17 @@ struct IcpUpdateArgs {
 void icp_update_launch(const IcpUpdateArgs& a, int64_t nhyp, cudaStream_t st);
 void icp_argmin_launch(const double* d_rmse, int64_t nhyp, int64_t* d_best, cudaStream_t st);
 
+// getLocalPoints.m batched over centres with the neighbourhoods left on the device (local_points.cu)
+struct LocalPointsDev {
+    std::vector<int64_t> counts, offsets;       // per centre: sphere count; rows offsets[k]..offsets[k+1]-1 (empty if rejected)
+    std::vector<int32_t> status;                // 1 where getLocalPoints returns []
+    DevBuf<double> pts;                         // [3][nel] points relative to their centre, original model order
+    DevBuf<int64_t> d_offsets;                  // offsets on the device
+    int64_t ntotal = 0, nel = 1;
+};
+void local_points_device(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, double R, int64_t min_points,
+                         int64_t max_points, LocalPointsDev& out, cudaStream_t st);
+
 void grid_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st);
 // MATLAB column-major 4x4 <-> internal row-major 4x4, batched (a transpose either way)
 void transpose16_launch(const double* d_in, double* d_out, int64_t n, cudaStream_t st);

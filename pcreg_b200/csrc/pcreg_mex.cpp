@@ -20,6 +20,11 @@
 //                                                      -> T, inlierIdx, numSuccess, maxInliers, pct  (ransac.m)
 //   'ransac_seeded', pts1, pts2, coef(struct incl. iterNum), seed
 //                                                      -> same five outputs, samples drawn on the device (pcreg_ransac_run)
+//   'local_points', handle, c(Kx3 double), R, min_points, max_points
+//                                                      -> pts_sphere (concatenated, relative to their centre), dists,
+//                                                         counts (Kx1; 0 where the reference returns [])   (getLocalPoints.m)
+//   'spatial_histogram', handle, sample_pts(Kx3 double), options(struct), r_bins, theta_bins, phi_bins
+//                                                      -> feat (Vx3), desc (Vx(nr*nt*np))     (getSpacialHistogramDescriptors.m)
 //   'icp', handle, src(Nx3), T0(4x4xH), opts(struct)[, w_src]
 //                                                      -> T(4x4xH), rmse(Hx1), n_used, status, best(1-based), idx(NxH)
 #include <string.h>
@@ -85,6 +90,89 @@ bool cmd_nn_search(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     double* o = mxGetPr(plhs[0]);
     for (int64_t i = 0; i < nq; ++i) o[i] = (double)idx[(size_t)i] + 1.0;
     if (nlhs > 1) plhs[1] = d2; else mxDestroyArray(d2);
+    return true;
+}
+
+bool cmd_local_points(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    pcreg_model* m = nrhs > 1 ? handle_of(prhs[1]) : nullptr;
+    if (!m || nrhs < 6 || !is_pts(prhs[2]) || !mxIsDouble(prhs[2])) { g_fail = "local_points: need (handle, c Kx3 double, R, min_points, max_points)"; return false; }
+    const int64_t nc = (int64_t)mxGetM(prhs[2]);
+    const double R = mxGetScalar(prhs[3]), mx = mxGetScalar(prhs[5]);
+    const int64_t min_points = (int64_t)mxGetScalar(prhs[4]);
+    const int64_t max_points = (mx > 9.0e18) ? -1 : (int64_t)mx;                 // inf (AlignPoints_c.m:14)
+    std::vector<int64_t> counts((size_t)nc), offsets((size_t)nc + 1, 0);
+    std::vector<int32_t> status((size_t)nc);
+    if (pcreg_local_points_count(m, mxGetPr(prhs[2]), nc, nc, R, min_points, max_points, counts.data(), status.data()) != PCREG_OK) {
+        g_fail = pcreg_last_error();
+        return false;
+    }
+    for (int64_t k = 0; k < nc; ++k) offsets[(size_t)k + 1] = offsets[(size_t)k] + (status[(size_t)k] ? 0 : counts[(size_t)k]);
+    const int64_t nt = offsets[(size_t)nc];
+    if (nt == 0) {                                                              // getLocalPoints.m:17-19,31-34: [] , []
+        plhs[0] = empty();
+        if (nlhs > 1) plhs[1] = empty();
+    } else {
+        mxArray* pts = mxCreateDoubleMatrix((mwSize)nt, 3, mxREAL);
+        mxArray* dists = mxCreateDoubleMatrix((mwSize)nt, 1, mxREAL);
+        if (pcreg_local_points_fill(m, mxGetPr(prhs[2]), nc, nc, R, offsets.data(), status.data(), mxGetPr(pts), nt, mxGetPr(dists), nullptr) != PCREG_OK) {
+            g_fail = pcreg_last_error();
+            mxDestroyArray(pts); mxDestroyArray(dists);
+            return false;
+        }
+        plhs[0] = pts;
+        if (nlhs > 1) plhs[1] = dists; else mxDestroyArray(dists);
+    }
+    if (nlhs > 2) {
+        plhs[2] = mxCreateDoubleMatrix((mwSize)nc, 1, mxREAL);
+        for (int64_t k = 0; k < nc; ++k) mxGetPr(plhs[2])[k] = status[(size_t)k] ? 0.0 : (double)counts[(size_t)k];
+    }
+    return true;
+}
+
+bool cmd_spatial_histogram(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    pcreg_model* m = nrhs > 1 ? handle_of(prhs[1]) : nullptr;
+    if (!m || nrhs < 7 || !is_pts(prhs[2]) || !mxIsDouble(prhs[2]) || !mxIsStruct(prhs[3]) || !mxIsDouble(prhs[4]) ||
+        !mxIsDouble(prhs[5]) || !mxIsDouble(prhs[6])) {
+        g_fail = "spatial_histogram: need (handle, sample_pts Kx3 double, options struct, r_bins, theta_bins, phi_bins)";
+        return false;
+    }
+    const mxArray* opt = prhs[3];
+    pcreg_desc_opts o;
+    pcreg_desc_opts_default(&o);
+    o.min_pts = (int64_t)field_or(opt, "min_pts", (double)o.min_pts);
+    const double mx = field_or(opt, "max_pts", (double)o.max_pts);
+    o.max_pts = (mx > 9.0e18) ? -1 : (int64_t)mx;
+    o.R = field_or(opt, "R", o.R);
+    const mxArray* th = mxGetField(opt, 0, "thVar");
+    if (th && mxIsDouble(th) && mxGetNumberOfElements(th) >= 2) { o.thVar[0] = mxGetPr(th)[0]; o.thVar[1] = mxGetPr(th)[1]; }
+    const mxArray* kf = mxGetField(opt, 0, "k");                                // 'all' or a fraction (getSpacialHistogramDescriptors.m:74)
+    o.k_frac = (kf && !mxIsChar(kf) && !mxIsEmpty(kf)) ? mxGetScalar(kf) : 0.0;
+    o.align_points = field_or(opt, "ALIGN_POINTS", 1.0) != 0.0;
+    const int nr = (int)mxGetNumberOfElements(prhs[4]) - 1, nt = (int)mxGetNumberOfElements(prhs[5]) - 1, np = (int)mxGetNumberOfElements(prhs[6]) - 1;
+    const int64_t nk = (int64_t)mxGetM(prhs[2]);
+    if (nr < 1 || nt < 1 || np < 1) { g_fail = "spatial_histogram: every edge vector needs at least two values"; return false; }
+    const int64_t nb = (int64_t)nr * nt * np;
+    std::vector<double> desc((size_t)nk * (size_t)nb);
+    std::vector<int32_t> status((size_t)nk);
+    if (pcreg_spatial_histogram(m, mxGetPr(prhs[2]), nk, nk, &o, mxGetPr(prhs[4]), nr, mxGetPr(prhs[5]), nt, mxGetPr(prhs[6]), np,
+                                desc.data(), status.data(), nullptr) != PCREG_OK) {
+        g_fail = pcreg_last_error();
+        return false;
+    }
+    int64_t nv = 0;
+    for (int64_t k = 0; k < nk; ++k) nv += status[(size_t)k] == 0;
+    // only the surviving keypoints, in keypoint order (getSpacialHistogramDescriptors.m:176-179)
+    plhs[0] = mxCreateDoubleMatrix((mwSize)nv, 3, mxREAL);
+    mxArray* D = mxCreateDoubleMatrix((mwSize)nv, (mwSize)nb, mxREAL);
+    const double* kp = mxGetPr(prhs[2]);
+    int64_t v = 0;
+    for (int64_t k = 0; k < nk; ++k) {
+        if (status[(size_t)k] != 0) continue;
+        for (int a = 0; a < 3; ++a) mxGetPr(plhs[0])[a * nv + v] = kp[a * nk + k];
+        for (int64_t j = 0; j < nb; ++j) mxGetPr(D)[j * nv + v] = desc[(size_t)k * (size_t)nb + (size_t)j];
+        ++v;
+    }
+    if (nlhs > 1) plhs[1] = D; else mxDestroyArray(D);
     return true;
 }
 
@@ -232,6 +320,8 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
         } else if (!strcmp(cmd, "model_create")) ok = cmd_model_create(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "model_destroy")) { pcreg_model_destroy(nrhs > 1 ? handle_of(prhs[1]) : nullptr); ok = true; if (nlhs > 0) plhs[0] = empty(); }
         else if (!strcmp(cmd, "nn_search")) ok = cmd_nn_search(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "local_points")) ok = cmd_local_points(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "spatial_histogram")) ok = cmd_spatial_histogram(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "align")) ok = cmd_align(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "estimate_transform")) ok = cmd_estimate_transform(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "ransac")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs, false);

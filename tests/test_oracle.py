@@ -154,3 +154,37 @@ def test_ransac_triplets_are_uniform_ordered_subsets():
     code = tri[:, 0] * 49 + tri[:, 1] * 7 + tri[:, 2]
     _, counts = np.unique(code, return_counts=True)
     assert counts.size == 210 and counts.min() > 0.7 * 60000 / 210 and counts.max() < 1.3 * 60000 / 210
+
+
+def test_histcounts_semantics_and_descriptor_layout():
+    """histcounts: left-closed bins, right border in the last bin, outside / NaN dropped (histcn.m:97-125); the descriptor
+    is reshape(counts, [], 1) of the r x theta x phi histogram (getSpacialHistogramDescriptors.m:161-164)."""
+    import oracle
+    e = np.array([0.0, 1.0, 2.0, 3.0])
+    x = np.array([-0.1, 0.0, 0.999, 1.0, 2.5, 3.0, 3.0001, np.nan])
+    assert oracle.histcounts_bin(x, e).tolist() == [0, 1, 1, 2, 3, 3, 0, 0]
+    r_bins, t_bins, p_bins = oracle.histogram_edges(3.5)
+    assert len(r_bins) == 11 and len(t_bins) == 8 and len(p_bins) == 15
+    np.testing.assert_allclose(np.diff(r_bins ** 3), 3.5 ** 3 / 10)            # equal-volume shells
+    # one point: r = 1, theta = pi/2 (z = 0), y > 0 -> phi = atan2(y, y) = pi/4
+    d = oracle.spatial_histogram_of(np.array([[0.6, 0.8, 0.0]]), 3.5, ALIGN_POINTS=False)
+    ir = int(np.searchsorted(r_bins, 1.0, side="right")) - 1
+    it, ip = 3, 8                                                              # pi/2 in [3pi/7, 4pi/7), pi/4 in bin 8 (0-based)
+    assert d.sum() == 1 and d[ir + 10 * (it + 7 * ip)] == 1
+
+
+def test_descriptor_is_rotation_invariant_up_to_binning():
+    """With ALIGN_POINTS the neighbourhood is expressed in its own disambiguated PCA frame, so a rigid rotation of the
+    cloud about the keypoint changes the histogram only where a point sits within rounding of a bin edge
+    (the purpose of the local reference frame; RotInvTests.m checks this by eye)."""
+    import oracle
+    from pcreg_b200 import synth
+    g = synth.rng(3)
+    nb = synth.make_neighbourhoods(1, 17, nmin=800, nmax=900, radius=3.5)[0]
+    nb = nb - nb.mean(axis=0) * 0.3
+    nb = nb[np.linalg.norm(nb, axis=1) < 3.5]
+    Rm = synth.rot_axis_angle(g.standard_normal(3), 0.9)
+    a = oracle.spatial_histogram_of(nb, 3.5, K=0.85, ALIGN_POINTS=True)
+    b = oracle.spatial_histogram_of(nb @ Rm, 3.5, K=0.85, ALIGN_POINTS=True)
+    assert a.sum() == b.sum() == nb.shape[0]
+    assert np.abs(a - b).sum() <= 4
