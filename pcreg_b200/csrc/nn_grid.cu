@@ -45,6 +45,7 @@ struct GridArgs {
     const unsigned int* in_count;   //                and how many
     int32_t* worklist;              // [nq] query ids handed to the next kernel (list -> direct -> walk)
     unsigned int* work_count;       // number of entries in worklist
+    unsigned long long* cursor;     // direct kernel: next unassigned position of its input (zeroed before the launch)
     int row_span;                   // direct kernel: widest (y,z) cell span it row-scans itself
     unsigned long long* counters;   // profiling only (may be null): [0] points / [1] rows visited by the row scan, [2] pyramid
                                     // nodes popped, [3] queries answered from their list, [4] queries walked, [5] queries
@@ -159,6 +160,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long* counters, uns
 // many active lanes too.
 constexpr int GRID_ROW_SPAN = 12;
 constexpr int GRID_FETCH_BATCH = 8;
+constexpr int GRID_CHUNK = 128;
 
 // (sqrt(best) + skin)^2, never too small: the points with d2 <= this value enter the candidate list
 __device__ __forceinline__ double list_thr2(double best, double skin) {
@@ -222,9 +224,11 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
         atomicAdd(&a.counters[5], (unsigned long long)total);
         if (a.in_list) atomicAdd(&a.counters[3], (unsigned long long)(a.nq - total));      // the list scan answered the rest
     }
-    const int64_t per_warp = (total + nwarps - 1) / nwarps;
-    int64_t next = warp_id * per_warp;                       // warp-uniform cursor into this warp's range
-    const int64_t end = min(total, next + per_warp);
+    // work is handed out in chunks of consecutive queries from a global cursor (the per-query cost varies by more
+    // than 10x, fixed ranges per warp leave a long tail); `next`..`end` is the warp's current chunk
+    int64_t next = 0, end = 0;
+    bool more = true;
+    (void)warp_id; (void)nwarps;
     const double inv_cell2 = G.inv_cell * G.inv_cell;
     const int dx0 = G.dims[0][0], dy0 = G.dims[0][1], dz0 = G.dims[0][2];
     unsigned long long n_pts = 0, n_cells = 0;
@@ -245,7 +249,14 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
         // ---- batched fetch ----
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
         const int nidle = __popc(idle);
-        if (next < end && (nidle >= GRID_FETCH_BATCH || nidle == 32 || (idle && end - next <= 0))) {
+        if (next >= end && more && nidle >= GRID_FETCH_BATCH) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)GRID_CHUNK);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((int64_t)base >= total) more = false;
+            else { next = (int64_t)base; end = min(total, next + GRID_CHUNK); }
+        }
+        if (next < end && (nidle >= GRID_FETCH_BATCH || nidle == 32)) {
             bool defer = false;
             if (!have) {
                 const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
@@ -281,7 +292,8 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
             worklist_append(a, defer, gq, lane);             // deferred queries go to the walk kernel
             continue;
         }
-        if (nidle == 32) break;                              // nothing in flight and nothing left to fetch
+        if (nidle == 32 && !more) break;                     // nothing in flight and nothing left to fetch
+        if (nidle == 32) continue;
         // ---- one trip: lanes out of points advance one row, then every lane with points processes one ----
         if (have && p >= e) {
             if (z > z1) {                                    // rows exhausted: done with this query
@@ -579,6 +591,9 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
             a.in_list = sc.worklist0.p; a.in_count = sc.count.p + 1;
         }
         a.worklist = sc.worklist.p; a.work_count = sc.count.p;
+        if (sc.cursor.n < 1) sc.cursor.alloc(1);
+        PCREG_CUDA(cudaMemsetAsync(sc.cursor.p, 0, sizeof(unsigned long long), st));
+        a.cursor = sc.cursor.p;
         mark(1);
         if (cl) k_nn_grid_direct<true><<<direct_blocks, 128, 0, st>>>(a);
         else    k_nn_grid_direct<false><<<direct_blocks, 128, 0, st>>>(a);

@@ -171,6 +171,7 @@ struct GridScratch {
     DevBuf<int32_t> worklist;       // [nq] direct -> walk
     DevBuf<int32_t> worklist0;      // [nq] list scan -> direct
     DevBuf<unsigned int> count;     // [2]
+    DevBuf<unsigned long long> cursor;   // [1] chunk cursor of the row-scan kernel
     // profiling: event marks between the kernels of a pass (kind 0 = list scan starts, 1 = row scan starts,
     // 2 = walk starts, 3 = pass ends); events are drawn from the pool through the caller's cursor
     struct Mark { int kind; cudaEvent_t ev; };
