@@ -46,6 +46,7 @@ struct GridArgs {
     int32_t* worklist;              // [nq] query ids handed to the next kernel (list -> direct -> walk)
     unsigned int* work_count;       // number of entries in worklist
     unsigned long long* cursor;     // direct kernel: next unassigned position of its input (zeroed before the launch)
+    int fetch_batch, chunk;         // (tuning)
     int row_span;                   // direct kernel: widest (y,z) cell span it row-scans itself
     unsigned long long* counters;   // profiling only (may be null): [0] points / [1] rows visited by the row scan, [2] pyramid
                                     // nodes popped, [3] queries answered from their list, [4] queries walked, [5] queries
@@ -160,7 +161,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long* counters, uns
 // many active lanes too.
 constexpr int GRID_ROW_SPAN = 12;
 constexpr int GRID_FETCH_BATCH = 8;
-constexpr int GRID_CHUNK = 128;
+constexpr int GRID_CHUNK = 32;
 
 // (sqrt(best) + skin)^2, never too small: the points with d2 <= this value enter the candidate list
 __device__ __forceinline__ double list_thr2(double best, double skin) {
@@ -249,14 +250,14 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
         // ---- batched fetch ----
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
         const int nidle = __popc(idle);
-        if (next >= end && more && nidle >= GRID_FETCH_BATCH) {
+        if (next >= end && more && nidle >= a.fetch_batch) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)GRID_CHUNK);
+            if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)a.chunk);
             base = __shfl_sync(0xffffffffu, base, 0);
             if ((int64_t)base >= total) more = false;
-            else { next = (int64_t)base; end = min(total, next + GRID_CHUNK); }
+            else { next = (int64_t)base; end = min(total, next + a.chunk); }
         }
-        if (next < end && (nidle >= GRID_FETCH_BATCH || nidle == 32)) {
+        if (next < end && (nidle >= a.fetch_batch || nidle == 32)) {
             bool defer = false;
             if (!have) {
                 const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
@@ -565,6 +566,9 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
     if (cl) a.cl = *cl;
     static const int row_span_env = [] { const char* e = getenv("PCREG_ROW_SPAN"); return e ? atoi(e) : 0; }();
     a.row_span = row_span_env > 0 ? row_span_env : GRID_ROW_SPAN;
+    static const int fb_env = [] { const char* e = getenv("PCREG_FETCH_BATCH"); return e ? atoi(e) : 0; }();
+    static const int ch_env = [] { const char* e = getenv("PCREG_CHUNK"); return e ? atoi(e) : 0; }();
+    a.fetch_batch = fb_env > 0 ? fb_env : GRID_FETCH_BATCH; a.chunk = ch_env > 0 ? ch_env : GRID_CHUNK;
     PCREG_REQUIRE(a.nq > 0, "nn_grid: no queries");
     PCREG_REQUIRE(a.nq < 2147483647LL, "nn_grid: too many queries in one launch");
     PCREG_REQUIRE(!cl || (int64_t)cl->cap * a.nq < ((int64_t)1 << 40), "nn_grid: candidate lists too large");
