@@ -51,7 +51,7 @@ int  pcreg_abi_version(void);
 typedef struct {
     int     build_grid;        /* 1: also build the uniform grid + occupancy pyramid (device counting sort) */
     double  cell_size;         /* grid cell edge; <= 0: automatic (about cells_per_point cells per point)   */
-    double  cells_per_point;   /* automatic sizing target, <= 0 -> 24                                       */
+    double  cells_per_point;   /* automatic sizing target, <= 0 -> 32                                       */
     int64_t max_cells;         /* cap on level-0 cells, <= 0 -> 2^27                                        */
     uint64_t shuffle_seed;     /* seed of the brute-force scan order permutation (any value; 0 is fine)     */
 } pcreg_model_opts;

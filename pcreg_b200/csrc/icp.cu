@@ -387,7 +387,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     // candidate lists (grid NN, nn_grid.cu): built by the full searches once a pose has nearly stopped moving,
     // scanned instead of searching while the query stays inside its list's guarantee.  PCREG_LISTS=0 disables.
     static const bool lists_on = [] { const char* e = getenv("PCREG_LISTS"); return !(e && e[0] == '0'); }();
-    static const double list_skin_cells = [] { const char* e = getenv("PCREG_LIST_SKIN"); return e ? atof(e) : 0.6; }();
+    static const double list_skin_cells = [] { const char* e = getenv("PCREG_LIST_SKIN"); return e ? atof(e) : 0.5; }();
     static const int list_cap = [] { const char* e = getenv("PCREG_LIST_CAP"); int v = e ? atoi(e) : 64; return std::max(4, (v + 3) & ~3); }();
     const bool use_lists = (o.nn == PCREG_NN_GRID) && lists_on && o.iters >= 3 && m->n <= ((int64_t)1 << 24);
     DevBuf<float4> cl_hdr(use_lists ? (size_t)hc * ns : 0);
@@ -442,7 +442,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         cl.ext = cl_ext.p; cl.ext_list = cl_ext_list.p; cl.ext_count = cl_ext_count.p; cl.ext_cap = ext_cap; cl.ext_slots = (int32_t)ext_slots;
         cl.gap_cells = (float)list_skin_cells;
         cl.skin = (double)cl.gap_cells * m->grid.cell * (1.0 - 1e-6);
-        static const double build_frac = [] { const char* e = getenv("PCREG_LIST_BUILD"); return e ? atof(e) : 1.0; }();
+        static const double build_frac = [] { const char* e = getenv("PCREG_LIST_BUILD"); return e ? atof(e) : 1.5; }();
         cl.build_max_delta = (float)(build_frac * cl.skin);
         cl.inv_level = (float)(255.0 / (2.0 * cl.skin));
         PCREG_CUDA(cudaMemsetAsync(delta.p, 0x7f, delta.bytes(), st));      // "large" until the first update writes it

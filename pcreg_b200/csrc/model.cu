@@ -258,7 +258,7 @@ void grid_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
     double cell = o.cell_size;
     if (!(cell > 0.0)) {
         static const double cpp_env = [] { const char* e = getenv("PCREG_CPP"); return e ? atof(e) : 0.0; }();
-        const double cpp = o.cells_per_point > 0.0 ? o.cells_per_point : (cpp_env > 0.0 ? cpp_env : 24.0);
+        const double cpp = o.cells_per_point > 0.0 ? o.cells_per_point : (cpp_env > 0.0 ? cpp_env : 32.0);
         const double cap = (double)(o.max_cells > 0 ? o.max_cells : ((int64_t)1 << 27));
         const double target = std::min(cap, std::max(64.0, cpp * (double)n));
         double vol = 1.0;

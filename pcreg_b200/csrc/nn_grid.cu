@@ -47,6 +47,7 @@ struct GridArgs {
     unsigned int* work_count;       // number of entries in worklist
     unsigned long long* cursor;     // direct kernel: next unassigned position of its input (zeroed before the launch)
     int fetch_batch, chunk;         // (tuning)
+    int chain;                      // first-pass walk: consecutive queries per thread
     int row_span;                   // direct kernel: widest (y,z) cell span it row-scans itself
     unsigned long long* counters;   // profiling only (may be null): [0] points / [1] rows visited by the row scan, [2] pyramid
                                     // nodes popped, [3] queries answered from their list, [4] queries walked, [5] queries
@@ -435,21 +436,21 @@ __global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArg
 // correspondences.  worklist == nullptr (first ICP pass, pcreg_nn_search): EVERY query, in chains of WALK_CHAIN
 // consecutive queries per thread -- the source cloud is spatially sorted, so the answer of one query is a tight
 // bound for the next and only the first query of a chain descends from the root.
-constexpr int WALK_CHAIN = 8;
+constexpr int WALK_CHAIN = 3;
 
 template <bool BUILD>
 __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ GridArgs a) {
     const GridView& G = a.g;
     const bool chained = (a.worklist == nullptr);
-    const int64_t count = chained ? (a.nq + WALK_CHAIN - 1) / WALK_CHAIN : (int64_t)*a.work_count;
+    const int64_t count = chained ? (a.nq + a.chain - 1) / a.chain : (int64_t)*a.work_count;
     if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters[4], (unsigned long long)(chained ? a.nq : count));
     const double inv_cell2 = G.inv_cell * G.inv_cell;
     unsigned long long n_pts = 0, n_cells = 0, n_nodes = 0;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < count; w += (int64_t)gridDim.x * blockDim.x) {
-        const int nchain = chained ? (int)min((int64_t)WALK_CHAIN, a.nq - w * WALK_CHAIN) : 1;
+        const int nchain = chained ? (int)min((int64_t)a.chain, a.nq - w * a.chain) : 1;
         int32_t warm = -1;
         for (int j = 0; j < nchain; ++j) {
-            const int64_t gq = chained ? w * WALK_CHAIN + j : (int64_t)a.worklist[w];
+            const int64_t gq = chained ? w * a.chain + j : (int64_t)a.worklist[w];
             if (!chained) warm = a.prev ? a.prev[gq] : -1;
             bool bld = false;
             int lc = 0, ext_slot = -1;
@@ -568,6 +569,8 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
     a.row_span = row_span_env > 0 ? row_span_env : GRID_ROW_SPAN;
     static const int fb_env = [] { const char* e = getenv("PCREG_FETCH_BATCH"); return e ? atoi(e) : 0; }();
     static const int ch_env = [] { const char* e = getenv("PCREG_CHUNK"); return e ? atoi(e) : 0; }();
+    static const int chain_env = [] { const char* e = getenv("PCREG_WALK_CHAIN"); return e ? atoi(e) : 0; }();
+    a.chain = chain_env > 0 ? chain_env : WALK_CHAIN;
     a.fetch_batch = fb_env > 0 ? fb_env : GRID_FETCH_BATCH; a.chunk = ch_env > 0 ? ch_env : GRID_CHUNK;
     PCREG_REQUIRE(a.nq > 0, "nn_grid: no queries");
     PCREG_REQUIRE(a.nq < 2147483647LL, "nn_grid: too many queries in one launch");
@@ -580,7 +583,9 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
         sc.timing->push_back(GridScratch::Mark{kind, ev});
     };
     const int64_t blocks = (a.nq + 127) / 128;
-    const int walk_blocks = (int)std::min<int64_t>(blocks, (int64_t)ctx().sm_count * 64);
+    static const int wcap_env = [] { const char* e = getenv("PCREG_WALK_CAP"); return e ? atoi(e) : 0; }();
+    const int64_t wcap = (int64_t)ctx().sm_count * (wcap_env > 0 ? wcap_env : 256);
+    const int walk_blocks = (int)std::min<int64_t>(blocks, wcap);
     if (d_prev) {
         if (sc.worklist.n < (size_t)a.nq) sc.worklist.alloc((size_t)a.nq);
         if (sc.count.n < 2) sc.count.alloc(2);
@@ -610,8 +615,8 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
         mark(3);
     } else {
         a.worklist = nullptr; a.work_count = nullptr;
-        const int64_t chains = (a.nq + WALK_CHAIN - 1) / WALK_CHAIN;
-        const int chain_blocks = (int)std::min<int64_t>((chains + 127) / 128, (int64_t)ctx().sm_count * 64);
+        const int64_t chains = (a.nq + a.chain - 1) / a.chain;
+        const int chain_blocks = (int)std::min<int64_t>((chains + 127) / 128, wcap);
         mark(2);
         k_nn_grid_walk<false><<<chain_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();
