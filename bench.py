@@ -245,8 +245,12 @@ def gpu_workload(P, torch, w, rank, steps, warmup, dist=None, world=1, e2e_steps
     sync_all()
     prof = P.last_profile()
     P.set_profiling(False)
+    ms_ranks = [ms / steps]
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        allms = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allms, tt)
+        ms_ranks = [float(x) / steps for x in allms.cpu()]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     rmse_best = float(out.rmse[int(out.best.item())].item())
@@ -293,7 +297,7 @@ def gpu_workload(P, torch, w, rank, steps, warmup, dist=None, world=1, e2e_steps
     m.destroy()
     q_per_step = H * ns * (w["iters"] + 1)
     return dict(ms_per_step=ms / steps, ms_per_step_e2e=ms_e2e / e2e_steps, q_per_step=q_per_step, H=H, ns=ns, launches=launches,
-                prof=prof, clocks=clocks, h2d=h2d, d2h=d2h, rmse_best=rmse_best, e2e_equals_device=ok_e2e, grid=grid,
+                prof=prof, clocks=clocks, ms_ranks=ms_ranks, h2d=h2d, d2h=d2h, rmse_best=rmse_best, e2e_equals_device=ok_e2e, grid=grid,
                 nm=model_h.shape[0])
 
 
@@ -387,7 +391,7 @@ def main():
                 e2e=dict(value=r["q_per_step"] * world / (r["ms_per_step_e2e"] * 1e-3), unit="queries/s", h2d_bytes_per_step=r["h2d"],
                          d2h_bytes_per_step=r["d2h"], ms_per_step=r["ms_per_step_e2e"], hyp_per_s=r["H"] * world / (r["ms_per_step_e2e"] * 1e-3),
                          result_equals_device_path=r["e2e_equals_device"]),
-                gpu_launches=r["launches"], clocks=r["clocks"], roofline=roofline_for(w, r),
+                gpu_launches=r["launches"], clocks=r["clocks"], ms_per_step_by_rank=r["ms_ranks"], roofline=roofline_for(w, r),
                 kernel_time_share=dict(nn_ms=r["prof"]["nn_ms"], update_ms=r["prof"]["update_ms"], list_ms=r["prof"]["list_ms"],
                                        rowscan_ms=r["prof"]["rowscan_ms"], walk_ms=r["prof"]["walk_ms"], step_ms=r["ms_per_step"],
                                        note="from one extra profiled step (event records + counters), not from the timed steps"),
