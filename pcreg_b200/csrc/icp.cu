@@ -370,6 +370,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + 28 + 4 * 64 + 4 * 448 / 16 : 0));
     const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)24 << 30, total_b / 6));
     int64_t hc = (int64_t)std::max<size_t>(1, budget / per_hyp);
+    if (const char* e = getenv("PCREG_MAX_CHUNK_HYP")) { const long v = atol(e); if (v > 0) hc = std::min<int64_t>(hc, v); }   // tests: force several chunks
     hc = std::min(hc, nhyp);
     hc = std::min<int64_t>(hc, 2147483647LL / std::max<int64_t>(1, ns) );       // int32 grid.x of per-query kernels stays safe
     hc = std::max<int64_t>(hc, 1);

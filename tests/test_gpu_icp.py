@@ -183,3 +183,39 @@ def test_icp_candidate_lists_are_exact_and_used(pcreg):
     assert np.array_equal(a["rmse_hist"], b["rmse_hist"])
     assert prof["certified_queries"] > 0.3 * prof["nn_queries"], prof
     m.destroy()
+
+
+def test_icp_chunked_hypotheses_identical(pcreg, monkeypatch):
+    """Large batches are processed in chunks of hypotheses (bounded scratch: correspondences, candidate lists, the
+    extension pool are per chunk).  Forcing 5 hypotheses per chunk must not change a single bit."""
+    model = synth.make_model(60_000, 77)
+    src, T_gt, c = synth.make_source(model, 1200, 0.3, 78)
+    T0 = synth.pose_grid(T_gt, c, 4, (2, 2, 2), 8.0, 1.5, 9)[:23]
+    m = pcreg.Model(model, grid=True)
+    a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    monkeypatch.setenv("PCREG_MAX_CHUNK_HYP", "5")
+    b = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    monkeypatch.delenv("PCREG_MAX_CHUNK_HYP")
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["best"] == b["best"]
+    m.destroy()
+
+
+def test_icp_wide_balls_use_extension_lists(pcreg):
+    """Source points far from the model (outliers the trim discards) have wide search balls: their candidate lists
+    overflow the 64-entry row into the extension pool.  Grid ICP must still equal brute-force ICP bit for bit."""
+    model = synth.make_model(150_000, 31)
+    src, T_gt, c = synth.make_source(model, 1500, 0.3, 32)
+    g = synth.rng(33)
+    src = np.vstack([src, src[:300] + g.normal(0, 2.5, (300, 3))])          # 17 % gross outliers, 2-6 mm off the surface
+    T0 = synth.pose_grid(T_gt, c, 2, (2, 2, 1), 5.0, 1.0, 9)
+    m = pcreg.Model(model, grid=True)
+    pcreg.set_profiling(True)
+    a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=25, nn=pcreg.NN_GRID, return_idx=True)
+    prof = pcreg.last_profile()
+    pcreg.set_profiling(False)
+    b = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=25, nn=pcreg.NN_BRUTE, return_idx=True)
+    assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["T"], b["T"]) and np.array_equal(a["rmse"], b["rmse"])
+    assert prof["certified_queries"] > 0.3 * prof["nn_queries"], prof
+    m.destroy()
