@@ -14,6 +14,7 @@
 #include <float.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 #include <algorithm>
 #include <vector>
 
@@ -363,42 +364,69 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     Context& c = ctx();
     const bool prof = c.profiling;
     for (int i = 0; i < 32; ++i) c.profile[i] = 0.0;
+    static const bool dbg_host = [] { const char* e = getenv("PCREG_DEBUG_HOST"); return e && e[0] == '1'; }();
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec; };
+    const double t_enter = now_ms();
+    double t_alloc = 0, t_sorted = 0, t_enq = 0;
 
     // chunk the hypotheses so that the per-correspondence scratch stays bounded
-    size_t free_b = 0, total_b = 0;
-    PCREG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t total_b = c.total_mem;         // queried once at pcreg_init (cudaMemGetInfo costs up to tens of ms per call)
     const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + 28 + 4 * 64 + 4 * 448 / 16 : 0));
     const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)24 << 30, total_b / 6));
-    int64_t hc = (int64_t)std::max<size_t>(1, budget / per_hyp);
+    // Two sub-batches ("lanes") on two streams: every kernel of the loop is latency bound with a tail (a few slow
+    // queries, a block per hypothesis), so the kernels of one lane fill the gaps of the other.  Profiling runs use one
+    // lane so that the per-kernel event times stay meaningful.  PCREG_LANES=1 disables.
+    const char* lanes_e = getenv("PCREG_LANES");                            // 1 = off, 2 = on whatever the batch size (tests)
+    const int lanes_env = lanes_e ? atoi(lanes_e) : 0;
+    const int nlanes = (prof || lanes_env == 1 || nhyp < 2 || (lanes_env != 2 && (double)nhyp * (double)ns < 2.0e6)) ? 1 : 2;
+    int64_t hc = (int64_t)std::max<size_t>(1, budget / (per_hyp * (size_t)nlanes));
     if (const char* e = getenv("PCREG_MAX_CHUNK_HYP")) { const long v = atol(e); if (v > 0) hc = std::min<int64_t>(hc, v); }   // tests: force several chunks
-    hc = std::min(hc, nhyp);
+    hc = std::min(hc, (nhyp + nlanes - 1) / nlanes);
     hc = std::min<int64_t>(hc, 2147483647LL / std::max<int64_t>(1, ns) );       // int32 grid.x of per-query kernels stays safe
     hc = std::max<int64_t>(hc, 1);
 
     DevBuf<double> Twork((size_t)nhyp * 16);
-    DevBuf<int32_t> idxA((size_t)hc * ns), idxB((size_t)hc * ns);
-    DevBuf<double> d2((size_t)hc * ns);
-    DevBuf<unsigned long long> keys(o.mode == PCREG_ICP_KNN ? (size_t)hc * ns : 0);
     DevBuf<int32_t> frozen((size_t)nhyp);
     DevBuf<double> rmse_tmp(d_rmse ? 0 : (size_t)nhyp);
     DevBuf<int32_t> nused_tmp(d_n_used ? 0 : (size_t)nhyp);
     DevBuf<unsigned long long> counters(16);
-    NNScratch scratch;
-    GridScratch gscratch;
     // candidate lists (grid NN, nn_grid.cu): built by the full searches once a pose has nearly stopped moving,
     // scanned instead of searching while the query stays inside its list's guarantee.  PCREG_LISTS=0 disables.
     static const bool lists_on = [] { const char* e = getenv("PCREG_LISTS"); return !(e && e[0] == '0'); }();
     static const double list_skin_cells = [] { const char* e = getenv("PCREG_LIST_SKIN"); return e ? atof(e) : 0.5; }();
     static const int list_cap = [] { const char* e = getenv("PCREG_LIST_CAP"); int v = e ? atoi(e) : 64; return std::max(4, (v + 3) & ~3); }();
     const bool use_lists = (o.nn == PCREG_NN_GRID) && lists_on && o.iters >= 3 && m->n <= ((int64_t)1 << 24);
-    DevBuf<float4> cl_hdr(use_lists ? (size_t)hc * ns : 0);
-    DevBuf<int2> cl_cnt(use_lists ? (size_t)hc * ns : 0);
-    DevBuf<int32_t> cl_list(use_lists ? (size_t)hc * ns * list_cap : 0);
-    DevBuf<float> delta(use_lists ? (size_t)nhyp : 0);
     const int ext_cap = 448;                                               // wide balls: up to list_cap + 448 candidates
     const int64_t ext_slots = use_lists ? std::max<int64_t>(1024, hc * ns / 16) : 0;
-    DevBuf<int32_t> cl_ext(use_lists ? (size_t)hc * ns : 0), cl_ext_list((size_t)ext_slots * ext_cap);
-    DevBuf<unsigned int> cl_ext_count(use_lists ? 1 : 0);
+    DevBuf<float> delta(use_lists ? (size_t)nhyp : 0);
+    struct Lane {
+        cudaStream_t st = nullptr;
+        DevBuf<int32_t> idxA, idxB, cl_list, cl_ext, cl_ext_list;
+        DevBuf<double> d2;
+        DevBuf<unsigned long long> keys;
+        DevBuf<float4> cl_hdr;
+        DevBuf<int2> cl_cnt;
+        DevBuf<unsigned int> cl_ext_count;
+        NNScratch scratch;
+        GridScratch gscratch;
+        CandView cl{};
+        int32_t* cur = nullptr; int32_t* prev = nullptr;
+        bool have_prev = false;
+        int64_t h0 = 0, hn = 0;
+    };
+    Lane lanes[2];
+    for (int l = 0; l < nlanes; ++l) {
+        Lane& L = lanes[l];
+        L.st = (nlanes == 1) ? st : lane_stream(l);
+        L.idxA.alloc((size_t)hc * ns); L.idxB.alloc((size_t)hc * ns); L.d2.alloc((size_t)hc * ns);
+        if (o.mode == PCREG_ICP_KNN) L.keys.alloc((size_t)hc * ns);
+        if (use_lists) {
+            L.cl_hdr.alloc((size_t)hc * ns); L.cl_cnt.alloc((size_t)hc * ns); L.cl_list.alloc((size_t)hc * ns * list_cap);
+            L.cl_ext.alloc((size_t)hc * ns); L.cl_ext_list.alloc((size_t)ext_slots * ext_cap); L.cl_ext_count.alloc(1);
+        }
+    }
+    GridScratch& gscratch = lanes[0].gscratch;
+    t_alloc = now_ms();
     DevBuf<double> src_stats(4);
     double* rm = d_rmse ? d_rmse : rmse_tmp.p;
     int32_t* nu = d_n_used ? d_n_used : nused_tmp.p;
@@ -434,65 +462,90 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         d_src = src_sorted.p;
         if (d_w) d_w = w_sorted.p;
     }
+    t_sorted = now_ms();
     const double* sx = d_src; const double* sy = d_src + ns; const double* sz = d_src + 2 * ns;
     k_src_stats<<<1, 1024, 0, st>>>(d_src, ns, src_stats.p);
     PCREG_LAUNCHED();
-    CandView cl{};
     if (use_lists) {
-        cl.hdr = cl_hdr.p; cl.cnt = cl_cnt.p; cl.list = cl_list.p; cl.cap = list_cap;
-        cl.ext = cl_ext.p; cl.ext_list = cl_ext_list.p; cl.ext_count = cl_ext_count.p; cl.ext_cap = ext_cap; cl.ext_slots = (int32_t)ext_slots;
-        cl.gap_cells = (float)list_skin_cells;
-        cl.skin = (double)cl.gap_cells * m->grid.cell * (1.0 - 1e-6);
         static const double build_frac = [] { const char* e = getenv("PCREG_LIST_BUILD"); return e ? atof(e) : 1.5; }();
-        cl.build_max_delta = (float)(build_frac * cl.skin);
-        cl.inv_level = (float)(255.0 / (2.0 * cl.skin));
+        for (int l = 0; l < nlanes; ++l) {
+            Lane& L = lanes[l];
+            CandView& cl = L.cl;
+            cl.hdr = L.cl_hdr.p; cl.cnt = L.cl_cnt.p; cl.list = L.cl_list.p; cl.cap = list_cap;
+            cl.ext = L.cl_ext.p; cl.ext_list = L.cl_ext_list.p; cl.ext_count = L.cl_ext_count.p; cl.ext_cap = ext_cap; cl.ext_slots = (int32_t)ext_slots;
+            cl.gap_cells = (float)list_skin_cells;
+            cl.skin = (double)cl.gap_cells * m->grid.cell * (1.0 - 1e-6);
+            cl.build_max_delta = (float)(build_frac * cl.skin);
+            cl.inv_level = (float)(255.0 / (2.0 * cl.skin));
+        }
         PCREG_CUDA(cudaMemsetAsync(delta.p, 0x7f, delta.bytes(), st));      // "large" until the first update writes it
     }
+    if (nlanes > 1) {                                                       // fork: the lanes start after everything queued on st
+        cudaEvent_t fork = pooled_event(ev_cursor++);
+        PCREG_CUDA(cudaEventRecord(fork, st));
+        for (int l = 0; l < nlanes; ++l) PCREG_CUDA(cudaStreamWaitEvent(lanes[l].st, fork, 0));
+    }
     double nn_launches = 0, upd_launches = 0;
-    for (int64_t h0 = 0; h0 < nhyp; h0 += hc) {
-        const int64_t hn = std::min(hc, nhyp - h0);
-        int32_t* cur = idxA.p; int32_t* prev = idxB.p;
-        bool have_prev = false;
-        if (use_lists) {
-            PCREG_CUDA(cudaMemsetAsync(cl_cnt.p, 0xff, (size_t)hn * ns * sizeof(int2), st));        // -1: no list yet
-            PCREG_CUDA(cudaMemsetAsync(cl_ext.p, 0xff, (size_t)hn * ns * sizeof(int32_t), st));     // -1: no extension slot
-            PCREG_CUDA(cudaMemsetAsync(cl_ext_count.p, 0, sizeof(unsigned int), st));
-            cl.delta = delta.p + h0;
+    for (int64_t base = 0; base < nhyp; base += hc * nlanes) {
+        for (int l = 0; l < nlanes; ++l) {
+            Lane& L = lanes[l];
+            L.h0 = std::min(nhyp, base + l * hc);
+            L.hn = std::min(hc, nhyp - L.h0);
+            L.cur = L.idxA.p; L.prev = L.idxB.p; L.have_prev = false;
+            if (use_lists && L.hn > 0) {
+                PCREG_CUDA(cudaMemsetAsync(L.cl_cnt.p, 0xff, (size_t)L.hn * ns * sizeof(int2), L.st));        // -1: no list yet
+                PCREG_CUDA(cudaMemsetAsync(L.cl_ext.p, 0xff, (size_t)L.hn * ns * sizeof(int32_t), L.st));     // -1: no extension slot
+                PCREG_CUDA(cudaMemsetAsync(L.cl_ext_count.p, 0, sizeof(unsigned int), L.st));
+                L.cl.delta = delta.p + L.h0;
+            }
         }
         for (int it = 0; it <= o.iters; ++it) {
             const bool last = (it == o.iters);
-            int32_t* out_idx = (last && d_idx && !sorted) ? d_idx + h0 * ns : cur;
-            ev_begin(0);
-            if (o.nn == PCREG_NN_BRUTE)
-                nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p, scratch, st);
-            else
-                nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, have_prev ? prev : nullptr, out_idx, d2.p,
-                               prof ? counters.p : nullptr, gscratch, use_lists ? &cl : nullptr, it >= 2, st);
-            ev_end();
-            nn_launches += 1;
-            IcpUpdateArgs ua{};
-            ua.md = m->md.p;
-            for (int k = 0; k < 3; ++k) ua.pivot[k] = m->pivot[k];
-            ua.sx = sx; ua.sy = sy; ua.sz = sz; ua.w_src = d_w; ua.ns = ns;
-            ua.T = Twork.p + h0 * 16; ua.idx = out_idx; ua.d2 = d2.p; ua.keys = keys.p;
-            ua.tie_order = sorted ? sinv.p : nullptr;
-            ua.delta = use_lists ? delta.p + h0 : nullptr;
-            ua.src_stats = src_stats.p;
-            ua.mode = o.mode; ua.k_frac = o.k_frac; ua.R_w = o.R_w; ua.thDist2 = o.thDist2; ua.reflection_fix = o.reflection_fix;
-            ua.update = last ? 0 : 1;
-            ua.frozen = frozen.p + h0; ua.rmse = rm + h0; ua.n_used = nu + h0;
-            ua.rmse_hist = d_rmse_hist ? d_rmse_hist + h0 * (o.iters + 1) : nullptr;
-            ua.hist_stride = o.iters + 1; ua.hist_col = it;
-            ev_begin(1);
-            icp_update_launch(ua, hn, st);
-            ev_end();
-            upd_launches += 1;
-            if (last && d_idx && sorted) {
-                k_unpermute_idx<<<(unsigned)((hn * ns + 255) / 256), 256, 0, st>>>(out_idx, sinv.p, ns, hn, d_idx + h0 * ns);
-                PCREG_LAUNCHED();
+            for (int l = 0; l < nlanes; ++l) {
+                Lane& L = lanes[l];
+                if (L.hn <= 0) continue;
+                cudaStream_t ls = L.st;
+                const int64_t h0 = L.h0, hn = L.hn;
+                int32_t* out_idx = (last && d_idx && !sorted) ? d_idx + h0 * ns : L.cur;
+                ev_begin(0);
+                if (o.nn == PCREG_NN_BRUTE)
+                    nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, L.have_prev ? L.prev : nullptr, out_idx, L.d2.p, L.scratch, ls);
+                else
+                    nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, L.have_prev ? L.prev : nullptr, out_idx, L.d2.p,
+                                   prof ? counters.p : nullptr, L.gscratch, use_lists ? &L.cl : nullptr, it >= 2, ls);
+                ev_end();
+                nn_launches += 1;
+                IcpUpdateArgs ua{};
+                ua.md = m->md.p;
+                for (int k = 0; k < 3; ++k) ua.pivot[k] = m->pivot[k];
+                ua.sx = sx; ua.sy = sy; ua.sz = sz; ua.w_src = d_w; ua.ns = ns;
+                ua.T = Twork.p + h0 * 16; ua.idx = out_idx; ua.d2 = L.d2.p; ua.keys = L.keys.p;
+                ua.tie_order = sorted ? sinv.p : nullptr;
+                ua.delta = use_lists ? delta.p + h0 : nullptr;
+                ua.src_stats = src_stats.p;
+                ua.mode = o.mode; ua.k_frac = o.k_frac; ua.R_w = o.R_w; ua.thDist2 = o.thDist2; ua.reflection_fix = o.reflection_fix;
+                ua.update = last ? 0 : 1;
+                ua.frozen = frozen.p + h0; ua.rmse = rm + h0; ua.n_used = nu + h0;
+                ua.rmse_hist = d_rmse_hist ? d_rmse_hist + h0 * (o.iters + 1) : nullptr;
+                ua.hist_stride = o.iters + 1; ua.hist_col = it;
+                ev_begin(1);
+                icp_update_launch(ua, hn, ls);
+                ev_end();
+                upd_launches += 1;
+                if (last && d_idx && sorted) {
+                    k_unpermute_idx<<<(unsigned)((hn * ns + 255) / 256), 256, 0, ls>>>(out_idx, sinv.p, ns, hn, d_idx + h0 * ns);
+                    PCREG_LAUNCHED();
+                }
+                std::swap(L.cur, L.prev);       // what was just written becomes the warm start
+                L.have_prev = true;
             }
-            std::swap(cur, prev);       // what was just written becomes the warm start
-            have_prev = true;
+        }
+    }
+    if (nlanes > 1) {                                                       // join
+        for (int l = 0; l < nlanes; ++l) {
+            cudaEvent_t done = pooled_event(ev_cursor++);
+            PCREG_CUDA(cudaEventRecord(done, lanes[l].st));
+            PCREG_CUDA(cudaStreamWaitEvent(st, done, 0));
         }
     }
     transpose16_launch(Twork.p, d_T16_cm, nhyp, st);
@@ -500,7 +553,10 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     if (d_best) icp_argmin_launch(rm, nhyp, d_best, st);
 
     // scratch is freed when this function returns: the stream must have drained
+    t_enq = now_ms();
     PCREG_CUDA(cudaStreamSynchronize(st));
+    if (dbg_host) fprintf(stderr, "[pcreg host] alloc %.2f  sort+sync %.2f  enqueue %.2f  drain %.2f ms\n", t_alloc - t_enter, t_sorted - t_alloc,
+                          t_enq - t_sorted, now_ms() - t_enq);
     if (prof) {
         double nn_ms = 0, upd_ms = 0;
         for (auto& e : evs) {

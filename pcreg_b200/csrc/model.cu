@@ -95,6 +95,15 @@ cudaEvent_t pooled_event(size_t i) {
     }
     return c.events[i];
 }
+cudaStream_t lane_stream(int i) {
+    Context& c = ctx();
+    while ((int)c.streams.size() <= i) {
+        cudaStream_t s;
+        PCREG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        c.streams.push_back(s);
+    }
+    return c.streams[i];
+}
 Context& ctx() { return g_ctx; }
 void require_init() {
     if (!g_ctx.initialised) throw ArgError{"pcreg_init has not been called (or failed): no CUDA device, and there is no CPU fallback"};
@@ -369,6 +378,7 @@ int pcreg_init(const int* devices, int ndev) {
     c.device = dev;
     c.sm_count = p.multiProcessorCount;
     c.smem_optin = p.sharedMemPerBlockOptin;
+    c.total_mem = p.totalGlobalMem;
     c.initialised = true;
     g_launches.store(0);
     return PCREG_OK;

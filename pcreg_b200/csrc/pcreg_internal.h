@@ -53,11 +53,14 @@ struct Context {
     int  device = 0;
     int  sm_count = 148;
     size_t smem_optin = 0;
+    size_t total_mem = 0;                // device memory, bytes
     bool profiling = false;
     double profile[32] = {0};
     std::vector<cudaEvent_t> events;     // reusable timing events (profiling mode)
+    std::vector<cudaStream_t> streams;   // internal streams of the two-lane ICP loop
 };
 cudaEvent_t pooled_event(size_t i);      // i-th reusable event, created on first use
+cudaStream_t lane_stream(int i);         // i-th internal stream (non-blocking), created on first use
 Context& ctx();
 void require_init();
 

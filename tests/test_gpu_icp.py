@@ -219,3 +219,24 @@ def test_icp_wide_balls_use_extension_lists(pcreg):
     assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["T"], b["T"]) and np.array_equal(a["rmse"], b["rmse"])
     assert prof["certified_queries"] > 0.3 * prof["nn_queries"], prof
     m.destroy()
+
+
+@pytest.mark.parametrize("nn", ["brute", "grid"])
+def test_icp_two_lanes_identical(pcreg, monkeypatch, nn):
+    """Large batches run as two sub-batches on two streams (icp.cu: lanes).  Forcing the two-lane schedule on a small
+    batch -- with an odd hypothesis count and several chunks per lane -- must not change a single bit."""
+    model = synth.make_model(60_000, 91)
+    src, T_gt, c = synth.make_source(model, 1100, 0.3, 92)
+    T0 = synth.pose_grid(T_gt, c, 4, (2, 2, 2), 8.0, 1.5, 9)[:27]
+    m = pcreg.Model(model, grid=True)
+    kind = pcreg.NN_GRID if nn == "grid" else pcreg.NN_BRUTE
+    monkeypatch.setenv("PCREG_LANES", "1")
+    a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=kind, return_idx=True, return_hist=True)
+    monkeypatch.setenv("PCREG_LANES", "2")
+    b = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=kind, return_idx=True, return_hist=True)
+    monkeypatch.setenv("PCREG_MAX_CHUNK_HYP", "4")
+    c2 = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=kind, return_idx=True, return_hist=True)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c2[k]), k
+    assert a["best"] == b["best"] == c2["best"]
+    m.destroy()
