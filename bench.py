@@ -39,6 +39,8 @@ WORKLOADS = {
                sigma=0.3, seed=1003, desc="C3 multi-start ICP: 4096 poses/GPU x 5k src vs 1M model, KNN-trimmed, 30 it, grid NN"),
     "c2": dict(nm=500_000, ns=10_000, hyp=1, iters=100, mode="weighted", nn="brute", rot=1, trans=(1, 1, 1), max_deg=0.0,
                sigma=0.3, seed=1002, desc="C2 AlignPoints_weighted-style single alignment: 10k weighted src vs 500k model, 100 it, brute NN"),
+    "c2g": dict(nm=500_000, ns=10_000, hyp=1, iters=100, mode="weighted", nn="grid", rot=1, trans=(1, 1, 1), max_deg=0.0,
+                sigma=0.3, seed=1002, desc="C2 with the grid NN path (same inputs and results as C2, what a user would run)"),
     "small": dict(nm=100_000, ns=2000, hyp=256, iters=10, mode="knn", nn="grid", rot=4, trans=(4, 4, 4), max_deg=10.0,
                   sigma=0.3, seed=7, desc="small multi-start ICP (debug)"),
 }
@@ -404,6 +406,11 @@ def main():
                           hyp_per_s=1.0 / s2, e2e=dict(value=r2["q_per_step"] / (r2["ms_per_step_e2e"] * 1e-3), unit="queries/s",
                                                        ms_per_step=r2["ms_per_step_e2e"]),
                           roofline=roofline_for(w2, r2), gpu_launches=r2["launches"], best_rmse=r2["rmse_best"], clocks=r2["clocks"])
+        w3 = WORKLOADS["c2g"]
+        r3 = gpu_workload(P, torch, w3, 0, max(2, args.steps), 3)
+        line["c2"]["grid_path"] = dict(workload=w3["desc"], value=r3["q_per_step"] / (r3["ms_per_step"] * 1e-3), unit="queries/s",
+                                       ms_per_step=r3["ms_per_step"], e2e_ms_per_step=r3["ms_per_step_e2e"], best_rmse=r3["rmse_best"],
+                                       same_result_as_brute=bool(r3["rmse_best"] == r2["rmse_best"]))
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         c = cpu_sample(w, budget_s=15.0)
