@@ -181,8 +181,9 @@ def test_descriptor_is_rotation_invariant_up_to_binning():
     from pcreg_b200 import synth
     g = synth.rng(3)
     nb = synth.make_neighbourhoods(1, 17, nmin=800, nmax=900, radius=3.5)[0]
-    nb = nb - nb.mean(axis=0) * 0.3
+    nb = nb - nb.mean(axis=0) + np.array([0.2, -0.1, 0.15])     # relative to a keypoint near (not at) the centroid
     nb = nb[np.linalg.norm(nb, axis=1) < 3.5]
+    assert nb.shape[0] > 500
     Rm = synth.rot_axis_angle(g.standard_normal(3), 0.9)
     a = oracle.spatial_histogram_of(nb, 3.5, K=0.85, ALIGN_POINTS=True)
     b = oracle.spatial_histogram_of(nb @ Rm, 3.5, K=0.85, ALIGN_POINTS=True)
