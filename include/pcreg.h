@@ -219,7 +219,8 @@ int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
  *   out[9] = pyramid nodes popped, out[10] = queries answered from their candidate list, out[11] = queries walked,
  *   out[12] = queries row-scanned, out[13] = list entries read, out[14] = list points gathered,
  *   out[15] = model points / out[16] = leaf cells visited by the walk;
- *   out[17..19] = total ms and out[20..22] = launches of the list-scan / row-scan / walk kernels.
+ *   out[17..19] = total ms and out[20..22] = launches of the list-scan / row-scan / walk kernels,
+ *   out[23] = queries whose search was skipped by lazy trimming (they are included in out[10]).
  * Collected only when enabled: the counters add atomics to the kernels, so timed runs keep it off. */
 int  pcreg_set_profiling(int enabled);
 int  pcreg_last_profile(double out[32]);

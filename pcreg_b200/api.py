@@ -401,7 +401,7 @@ def last_profile() -> dict:
     v = list(buf)
     return dict(nn_launches=v[0], nn_ms=v[1], nn_queries=v[2], brute_pairs=v[3], update_launches=v[4],
                 update_ms=v[5], correspondences=v[6], grid_points_visited=v[7] + v[15], grid_cells_visited=v[8] + v[16],
-                grid_nodes_popped=v[9], certified_queries=v[10], walked_queries=v[11], rowscan_queries=v[12],
+                grid_nodes_popped=v[9], certified_queries=v[10] - v[23], lazy_skipped_queries=v[23], walked_queries=v[11], rowscan_queries=v[12],
                 list_entries_read=v[13], list_points_gathered=v[14],
                 rowscan_points=v[7], rowscan_rows=v[8], walk_points=v[15], walk_leaves=v[16],
                 list_ms=v[17], rowscan_ms=v[18], walk_ms=v[19], list_launches=v[20], rowscan_launches=v[21], walk_launches=v[22])

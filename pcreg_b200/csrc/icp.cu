@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_cons
 
     unsigned long long vK = 0ull;
     bool all_eq = false;
+    double trim_tau = INFINITY;             // KNN mode: the largest selected residual (K-th smallest distance)
     if (a.mode == PCREG_ICP_KNN) {
         unsigned long long* __restrict__ keys = a.keys + h * ns;
         long long nkept = 0;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_cons
         long long K = (long long)floor(a.k_frac * (double)nkept + 0.5);     // MATLAB round (AlignPoints_KNN.m:21)
         if (K > nkept) K = nkept;
         block_hist_select(keys, ns, K, kmin, kmax, hsel, vK, all_eq, a.tie_order);
+        if (!reject && K >= 1 && K < nkept && nkept == ns) trim_tau = __longlong_as_double((long long)vK);
     }
 
     // ---- weights + the 17 sums ----
@@ -184,6 +186,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_cons
             }
         }
         if (a.delta) a.delta[h] = moved;
+        // Lazy trimming (nn_grid.cu, k_nn_list): the NN distance is 1-Lipschitz in the query position and the next pass
+        // moves no query by more than `moved`, so the K selected residuals stay <= tau + moved; a query whose residual
+        // was > tau + 2 moved stays strictly outside the selected set and its search can be skipped in the next pass.
+        if (a.skip_thr) a.skip_thr[h] = (a.update && a.delta) ? (trim_tau + 2.0 * (double)moved) * (1.0 + 1e-9) : INFINITY;
     }
 }
 
@@ -399,6 +405,10 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     const int ext_cap = 448;                                               // wide balls: up to list_cap + 448 candidates
     const int64_t ext_slots = use_lists ? std::max<int64_t>(1024, hc * ns / 16) : 0;
     DevBuf<float> delta(use_lists ? (size_t)nhyp : 0);
+    // lazy trimming: residual above which a query of hypothesis h cannot be selected in the next pass (update kernel)
+    static const bool lazy_on = [] { const char* e = getenv("PCREG_LAZY_TRIM"); return !(e && e[0] == '0'); }();
+    const bool lazy_trim = use_lists && lazy_on && o.mode == PCREG_ICP_KNN && !(o.thDist2 > 0.0);
+    DevBuf<double> skip_thr(lazy_trim ? (size_t)nhyp : 0);
     struct Lane {
         cudaStream_t st = nullptr;
         DevBuf<int32_t> idxA, idxB, cl_list, cl_ext, cl_ext_list;
@@ -479,6 +489,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             cl.inv_level = (float)(255.0 / (2.0 * cl.skin));
         }
         PCREG_CUDA(cudaMemsetAsync(delta.p, 0x7f, delta.bytes(), st));      // "large" until the first update writes it
+        if (lazy_trim) PCREG_CUDA(cudaMemsetAsync(skip_thr.p, 0x7f, skip_thr.bytes(), st));
     }
     if (nlanes > 1) {                                                       // fork: the lanes start after everything queued on st
         cudaEvent_t fork = pooled_event(ev_cursor++);
@@ -512,7 +523,8 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
                     nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, L.have_prev ? L.prev : nullptr, out_idx, L.d2.p, L.scratch, ls);
                 else
                     nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, L.have_prev ? L.prev : nullptr, out_idx, L.d2.p,
-                                   prof ? counters.p : nullptr, L.gscratch, use_lists ? &L.cl : nullptr, it >= 2, ls);
+                                   prof ? counters.p : nullptr, L.gscratch, use_lists ? &L.cl : nullptr, it >= 2,
+                                   (lazy_trim && it >= 2 && !last) ? skip_thr.p + h0 : nullptr, ls);
                 ev_end();
                 nn_launches += 1;
                 IcpUpdateArgs ua{};
@@ -522,6 +534,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
                 ua.T = Twork.p + h0 * 16; ua.idx = out_idx; ua.d2 = L.d2.p; ua.keys = L.keys.p;
                 ua.tie_order = sorted ? sinv.p : nullptr;
                 ua.delta = use_lists ? delta.p + h0 : nullptr;
+                ua.skip_thr = lazy_trim ? skip_thr.p + h0 : nullptr;
                 ua.src_stats = src_stats.p;
                 ua.mode = o.mode; ua.k_frac = o.k_frac; ua.R_w = o.R_w; ua.thDist2 = o.thDist2; ua.reflection_fix = o.reflection_fix;
                 ua.update = last ? 0 : 1;
@@ -568,6 +581,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         unsigned long long hcnt[16] = {0};
         PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
         for (int k = 3; k < 10; ++k) c.profile[7 + k] = (double)hcnt[k];       // out[10..16]
+        c.profile[23] = (double)hcnt[10];                                       // queries skipped by lazy trimming
         // per-kernel time of the grid path: the span from each mark to the next one of the same pass
         for (size_t k = 0; k + 1 < marks.size(); ++k) {
             if (marks[k].kind == 3) continue;
@@ -677,7 +691,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         nn_brute_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p, scratch, st);
     else
         nn_grid_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p,
-                       c.profiling ? counters.p : nullptr, gscratch, nullptr, false, st);
+                       c.profiling ? counters.p : nullptr, gscratch, nullptr, false, nullptr, st);
     if (c.profiling) PCREG_CUDA(cudaEventRecord(e1, st));
     PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
     if (d2) PCREG_CUDA(cudaMemcpyAsync(d2, d_d2.p, d_d2.bytes(), cudaMemcpyDeviceToHost, st));

@@ -41,6 +41,7 @@ struct GridArgs {
     const int32_t* prev;
     int32_t* idx; double* d2;
     CandView cl;                    // candidate lists of the chunk (cl.cnt == nullptr: disabled)
+    const double* skip_thr;         // [nhyp] or null: list kernel skips queries whose previous residual exceeds it (lazy trimming)
     const int32_t* in_list;         // direct kernel: the queries to process (nullptr: all nq)
     const unsigned int* in_count;   //                and how many
     int32_t* worklist;              // [nq] query ids handed to the next kernel (list -> direct -> walk)
@@ -134,7 +135,8 @@ __device__ __forceinline__ void scan_points(const GridView& G, int32_t s0, int32
 }
 
 __device__ __forceinline__ void flush_counters(unsigned long long* counters, unsigned long long n_pts,
-                                               unsigned long long n_cells, unsigned long long n_nodes, int i_pts = 0, int i_cells = 1) {
+                                               unsigned long long n_cells, unsigned long long n_nodes, int i_pts = 0, int i_cells = 1,
+                                               int i_nodes = 2) {
     if (!counters) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -145,7 +147,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long* counters, uns
     if ((threadIdx.x & 31) == 0) {
         if (n_pts) atomicAdd(&counters[i_pts], n_pts);
         if (n_cells) atomicAdd(&counters[i_cells], n_cells);
-        if (n_nodes) atomicAdd(&counters[2], n_nodes);
+        if (n_nodes) atomicAdd(&counters[i_nodes], n_nodes);
     }
 }
 
@@ -392,7 +394,22 @@ __global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArg
     const int64_t gq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool defer = false;
     unsigned n_read = 0, n_gather = 0;
-    if (gq < a.nq) {
+    bool skipped = false;
+    if (gq < a.nq && a.skip_thr) {
+        // Lazy trimming: this query's residual was so far above the hypothesis' trim threshold that it cannot be among the
+        // selected correspondences of this pass either (icp.cu).  Its correspondence is carried over and its residual
+        // replaced by a lower bound (previous residual minus the largest possible motion), which keeps it out of the
+        // selection and makes the same test valid in the next pass.
+        const unsigned h = (unsigned)gq / (unsigned)a.ns;
+        const double sd = sqrt(a.d2[gq]);
+        if (sd * (1.0 - 1e-12) > a.skip_thr[h]) {
+            const double nl = sd * (1.0 - 1e-12) - (double)a.cl.delta[h] * (1.0 + 1e-6);
+            a.d2[gq] = nl * nl * (1.0 - 1e-12);
+            a.idx[gq] = a.prev[gq];
+            skipped = true;
+        }
+    }
+    if (gq < a.nq && !skipped) {
         const int2 cs = a.cl.cnt[gq];
         const int cnt = cs.x;
         if (cnt <= 0) {
@@ -428,7 +445,7 @@ __global__ void __launch_bounds__(128) k_nn_list(const __grid_constant__ GridArg
         }
     }
     worklist_append(a, defer, gq, lane);
-    if (a.counters) flush_counters(a.counters, n_read, n_gather, 0, 6, 7);
+    if (a.counters) flush_counters(a.counters, n_read, n_gather, skipped ? 1ull : 0ull, 6, 7, 10);
 }
 
 // ---- kernel 2: pyramid walk --------------------------------------------------------------------------------
@@ -558,13 +575,15 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
 
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz, int64_t ns,
                     const double* d_T, int64_t nhyp, const int32_t* d_prev, int32_t* d_idx, double* d_d2,
-                    unsigned long long* d_counters, GridScratch& sc, const CandView* cl, bool scan_lists, cudaStream_t st) {
+                    unsigned long long* d_counters, GridScratch& sc, const CandView* cl, bool scan_lists, const double* d_skip_thr,
+                    cudaStream_t st) {
     PCREG_REQUIRE(m->has_grid, "grid NN requested but the model was created without build_grid");
     GridArgs a{};
     a.g = m->grid; a.md = m->md.p;
     a.sx = d_sx; a.sy = d_sy; a.sz = d_sz; a.ns = ns; a.T = d_T; a.nq = nhyp * ns;
     a.prev = d_prev; a.idx = d_idx; a.d2 = d_d2; a.counters = d_counters;
     if (cl) a.cl = *cl;
+    a.skip_thr = (cl && scan_lists && d_prev) ? d_skip_thr : nullptr;
     static const int row_span_env = [] { const char* e = getenv("PCREG_ROW_SPAN"); return e ? atoi(e) : 0; }();
     a.row_span = row_span_env > 0 ? row_span_env : GRID_ROW_SPAN;
     static const int fb_env = [] { const char* e = getenv("PCREG_FETCH_BATCH"); return e ? atoi(e) : 0; }();

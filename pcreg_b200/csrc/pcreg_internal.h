@@ -185,7 +185,7 @@ struct GridScratch {
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz,
                     int64_t ns, const double* d_T, int64_t nhyp, const int32_t* d_prev,
                     int32_t* d_idx, double* d_d2, unsigned long long* d_visit_counters, GridScratch& scratch,
-                    const CandView* cl, bool scan_lists, cudaStream_t st);
+                    const CandView* cl, bool scan_lists, const double* d_skip_thr /*[nhyp] or null: lazy trimming*/, cudaStream_t st);
 
 // Select / weight / 17 sums / Kabsch / compose, one block per hypothesis.
 struct IcpUpdateArgs {
@@ -199,6 +199,7 @@ struct IcpUpdateArgs {
     const int32_t* tie_order;   // [ns] or null: tie_order[original index] = position in the (sorted) source arrays
     float* delta;               // [nhyp] or null: out, upper bound of the displacement of any source point by this update
     const double* src_stats;    // [4] centroid + radius of the source cloud (for delta)
+    double* skip_thr;           // [nhyp] or null: out, residual above which a query cannot be selected in the next pass
     int mode; double k_frac; double R_w; double thDist2; int reflection_fix;
     int update;                 // 1: apply the pose update; 0: score only (final pass)
     int32_t* frozen;            // [nhyp] status flags (1 = frozen)

@@ -218,6 +218,9 @@ def test_icp_wide_balls_use_extension_lists(pcreg):
     b = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=25, nn=pcreg.NN_BRUTE, return_idx=True)
     assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["T"], b["T"]) and np.array_equal(a["rmse"], b["rmse"])
     assert prof["certified_queries"] > 0.3 * prof["nn_queries"], prof
+    # lazy trimming: most of the gross outliers are provably outside the 85 % trim from one pass to the next, their
+    # searches are skipped (yet the final correspondences above are exact, and the poses identical to brute force)
+    assert prof["lazy_skipped_queries"] > 0.05 * prof["nn_queries"], prof
     m.destroy()
 
 
