@@ -189,7 +189,18 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_cons
         // Lazy trimming (nn_grid.cu, k_nn_list): the NN distance is 1-Lipschitz in the query position and the next pass
         // moves no query by more than `moved`, so the K selected residuals stay <= tau + moved; a query whose residual
         // was > tau + 2 moved stays strictly outside the selected set and its search can be skipped in the next pass.
-        if (a.skip_thr) a.skip_thr[h] = (a.update && a.delta) ? (trim_tau + 2.0 * (double)moved) * (1.0 + 1e-9) : INFINITY;
+        // The same holds for a rejection threshold (residual >= sqrt(thDist2) + moved stays rejected) and for the
+        // weighted mode (residual >= R_w + moved keeps weight zero).  With a rejection threshold the number of kept
+        // correspondences, hence K, may change from pass to pass, so the trim bound is only used without one.
+        if (a.skip_thr) {
+            double thr = INFINITY;
+            if (a.update && a.delta) {
+                thr = (trim_tau + 2.0 * (double)moved) * (1.0 + 1e-9);
+                if (reject) thr = fmin(thr, (sqrt(a.thDist2) + (double)moved) * (1.0 + 1e-9));
+                if (a.mode == PCREG_ICP_WEIGHTED) thr = fmin(thr, (a.R_w + (double)moved) * (1.0 + 1e-9));
+            }
+            a.skip_thr[h] = thr;
+        }
     }
 }
 
@@ -407,7 +418,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     DevBuf<float> delta(use_lists ? (size_t)nhyp : 0);
     // lazy trimming: residual above which a query of hypothesis h cannot be selected in the next pass (update kernel)
     static const bool lazy_on = [] { const char* e = getenv("PCREG_LAZY_TRIM"); return !(e && e[0] == '0'); }();
-    const bool lazy_trim = use_lists && lazy_on && o.mode == PCREG_ICP_KNN && !(o.thDist2 > 0.0);
+    const bool lazy_trim = use_lists && lazy_on && (o.mode == PCREG_ICP_KNN || o.mode == PCREG_ICP_WEIGHTED || o.thDist2 > 0.0);
     DevBuf<double> skip_thr(lazy_trim ? (size_t)nhyp : 0);
     struct Lane {
         cudaStream_t st = nullptr;
