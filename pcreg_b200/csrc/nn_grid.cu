@@ -10,10 +10,15 @@
 //                     exactly.  A point outside the list is farther than R_list - |q - q0| from the moved
 //                     query, so when the best list distance is below that the list answer is the exact
 //                     nearest neighbour (ties included).  Everything else goes to the next kernel.
+//                     Entries carry the level of their build-time distance, so candidates that cannot have
+//                     become the nearest one are skipped without a gather; queries that are provably outside
+//                     the trim / beyond the rejection threshold of this pass are not searched at all (lazy
+//                     trimming, see the kernel).
 //   k_nn_grid_direct  warm-started queries whose ball (radius = distance to the previous iteration's
-//                     correspondence) has a bounding cube of at most 4 x 4 x 4 level-0 cells: the <= 16
-//                     (y,z) cell rows are contiguous point runs, fetched with independent loads and
-//                     scanned.  Everything else is appended to a work list (warp-aggregated atomics).
+//                     correspondence) spans at most GRID_ROW_SPAN level-0 cells in y and z: every (y,z) cell
+//                     row the ball reaches is one contiguous run of points.  Persistent warps, one small state
+//                     machine per lane, work drawn in 32-query chunks from a global cursor.  Everything else
+//                     is appended to a work list (warp-aggregated atomics).
 //                     BUILD variant: the scan is exhaustive within (best distance + gap) and the points within
 //                     (best distance + skin) become the query's new candidate list.
 //   k_nn_grid_walk    branch-and-bound walk of the occupancy pyramid with a small explicit stack for the
