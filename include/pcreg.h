@@ -107,6 +107,30 @@ int  pcreg_spatial_histogram(const pcreg_model* m, const double* keypoints, int6
                              const pcreg_desc_opts* opts, const double* r_edges, int nr, const double* theta_edges, int nt,
                              const double* phi_edges, int np, double* desc, int32_t* status, int64_t* counts);
 
+/* ---- getMatches.m:1-56: descriptor weighting + matchFeatures, EXHAUSTIVE search ------------------------- */
+#define PCREG_METRIC_SAD 0
+#define PCREG_METRIC_SSD 1
+typedef struct {
+    int    unnormalize;      /* par.UNNORMALIZE: append norm_factor * mean 1-norm as an extra element (getMatches.m:22-27) */
+    double norm_factor;      /* par.norm_factor (2, completeExperiment.m:113)                                            */
+    int    change_metric;    /* par.CHANGE_METRIC: element-wise power before matching (getMatches.m:35-37)               */
+    double metric_factor;    /* par.metric_factor (0.6, completeExperiment.m:116)                                        */
+    double match_threshold;  /* par.MatchThreshold, percent of the largest possible score (10)                           */
+    double max_ratio;        /* par.MaxRatio: nearest / second nearest score (0.99)                                      */
+    int    metric;           /* par.Metric: PCREG_METRIC_SAD ('SAD') or PCREG_METRIC_SSD ('SSD')                          */
+    int    unique;           /* par.Unique: forward-backward 1-to-1 matches only                                         */
+} pcreg_match_opts;
+void pcreg_match_opts_default(pcreg_match_opts* o);      /* the values of completeExperiment.m:112-122 */
+/* desc_surface: n1 x dim, desc_model: n2 x dim, COLUMN-MAJOR doubles (element (i,k) at [k*ld + i]) -- the matrices
+ * getSpacialHistogramDescriptors returns.  matchFeatures semantics (documentation, 'Method','Exhaustive'): rows are
+ * normalised to unit vectors, every surface descriptor is paired with its nearest model descriptor (first index on
+ * ties), pairs above MatchThreshold, above MaxRatio or (Unique) not mutually nearest are dropped.  par.Method =
+ * 'Approximate' (the reference's setting) is a randomised kd-forest of the closed toolbox: this is the search it
+ * approximates.  Outputs: index_pairs [n1][2] (pair p = {surface row, model row}, 0-based, ascending surface row;
+ * first *n_matches valid), match_metric [n1] (optional: the score of each pair). */
+int  pcreg_get_matches(const double* desc_surface, int64_t n1, int64_t ld1, const double* desc_model, int64_t n2, int64_t ld2,
+                       int64_t dim, const pcreg_match_opts* opts, int32_t* index_pairs, double* match_metric, int64_t* n_matches);
+
 /* ---- AlignPoints family (AlignPoints.m:1-29, AlignPoints_KNN.m:1-60, AlignPoints_knn.m:1-43,
  *      AlignPoints_weighted.m:1-49, AlignPoints_c.m:1-44, AlignPoints_KNN_c.m:1-57), batched over
  *      neighbourhoods ---------------------------------------------------------------------------- */
@@ -220,7 +244,8 @@ int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
  *   out[12] = queries row-scanned, out[13] = list entries read, out[14] = list points gathered,
  *   out[15] = model points / out[16] = leaf cells visited by the walk;
  *   out[17..19] = total ms and out[20..22] = launches of the list-scan / row-scan / walk kernels,
- *   out[23] = queries whose search was skipped by lazy trimming (they are included in out[10]).
+ *   out[23] = queries whose search was skipped by lazy trimming (they are included in out[10]);
+ *   after pcreg_get_matches: out[24] = total ms of the score kernel, out[25] = (pair, dimension) terms it evaluated.
  * Collected only when enabled: the counters add atomics to the kernels, so timed runs keep it off. */
 int  pcreg_set_profiling(int enabled);
 int  pcreg_last_profile(double out[32]);

@@ -15,6 +15,8 @@ Parity status (see DESIGN.md section "Oracle"):
     .m files; MATLAB built-ins (pca/eig/sort/rank/round) restated from their
     documentation.  MATLAB/Octave are not installed here, so these are
     "parity unpinned" beyond algebraic identities.
+  * getMatches: the weighting lines restated from getMatches.m; matchFeatures (closed toolbox, 'Approximate' in the
+    reference's drivers) restated from its documentation as the exhaustive search.  PARITY UNPINNED.
   * Nearest-neighbour step and the composed ICP: the reference has no such
     code; semantics = MATLAB knnsearch documentation
     (Euclidean, FP64, K=1, ties -> smallest index).  PARITY UNPINNED.
@@ -28,5 +30,6 @@ from .align import (  # noqa: F401
     AlignPoints_c, AlignPoints_KNN_c,
 )
 from .descriptors import getSpacialHistogramDescriptors, spatial_histogram_of, histogram_edges, histcn3, histcounts_bin  # noqa: F401
+from .matching import getMatches, match_features_exhaustive, weight_descriptors  # noqa: F401
 from .nn import nn_brute, nn_kdtree  # noqa: F401
 from .icp import icp_single, icp_batch, ICP_PLAIN, ICP_KNN, ICP_WEIGHTED  # noqa: F401

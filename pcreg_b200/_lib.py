@@ -36,6 +36,11 @@ class DescOpts(C.Structure):
                 ("k_frac", C.c_double), ("align_points", C.c_int)]
 
 
+class MatchOpts(C.Structure):
+    _fields_ = [("unnormalize", C.c_int), ("norm_factor", C.c_double), ("change_metric", C.c_int), ("metric_factor", C.c_double),
+                ("match_threshold", C.c_double), ("max_ratio", C.c_double), ("metric", C.c_int), ("unique", C.c_int)]
+
+
 class RansacOpts(C.Structure):
     _fields_ = [("thDist", C.c_double), ("thInlrRatio", C.c_double), ("refine", C.c_int), ("reflection_fix", C.c_int)]
 
@@ -63,6 +68,9 @@ SIGNATURES = {
     "pcreg_desc_opts_default": (None, [C.POINTER(DescOpts)]),
     "pcreg_spatial_histogram": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.POINTER(DescOpts), c_f64p, C.c_int, c_f64p, C.c_int,
                                           c_f64p, C.c_int, c_f64p, c_i32p, c_i64p]),
+    "pcreg_match_opts_default": (None, [C.POINTER(MatchOpts)]),
+    "pcreg_get_matches": (C.c_int, [c_f64p, C.c_int64, C.c_int64, c_f64p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(MatchOpts),
+                                    c_i32p, c_f64p, c_i64p]),
     "pcreg_align_opts_default": (None, [C.POINTER(AlignOpts)]),
     "pcreg_align_points": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, c_i64p, C.c_int64, C.POINTER(AlignOpts),
                                      C.c_void_p, c_f64p, c_f64p, c_i32p]),

@@ -14,10 +14,11 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import AlignOpts, DescOpts, IcpOpts, ModelOpts, PcregError, RansacOpts  # noqa: F401
+from ._lib import AlignOpts, DescOpts, IcpOpts, MatchOpts, ModelOpts, PcregError, RansacOpts  # noqa: F401
 
 NN_BRUTE, NN_GRID = 0, 1
 ICP_PLAIN, ICP_KNN, ICP_WEIGHTED = 0, 1, 2
+METRIC_SAD, METRIC_SSD = 0, 1
 ALIGN_PLAIN, ALIGN_KNN_FRAC, ALIGN_KNN_ABS, ALIGN_WEIGHTED, ALIGN_C, ALIGN_KNN_C = range(6)
 
 
@@ -193,6 +194,50 @@ def getSpacialHistogramDescriptors(pts, sample_pts, options, return_status=False
     finally:
         if own:
             m.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# getMatches
+# ------------------------------------------------------------------------------------------------
+def getMatches(descSurface, descModel, par: dict, return_metric=False):
+    """getMatches.m:1-56 -> matches [P, 2] (0-based rows of descSurface / descModel, ascending surface row).
+
+    `par` is the reference's struct as a dict: UNNORMALIZE, norm_factor, CHANGE_METRIC, metric_factor, Method,
+    MatchThreshold, MaxRatio, Metric ('SAD' | 'SSD'), Unique.  par['Method'] is accepted and ignored: the search is
+    exhaustive (what matchFeatures' 'Approximate' kd-forest approximates).  With return_metric also the score of
+    every pair (matchFeatures' second output)."""
+    d1 = np.asfortranarray(np.asarray(descSurface, dtype=np.float64))
+    d2 = np.asfortranarray(np.asarray(descModel, dtype=np.float64))
+    if d1.ndim != 2 or d2.ndim != 2 or d1.shape[1] != d2.shape[1]:
+        raise ValueError("descriptors must be N1 x D and N2 x D")
+    n1, n2, dim = d1.shape[0], d2.shape[0], d1.shape[1]
+    o = MatchOpts()
+    L.lib().pcreg_match_opts_default(C.byref(o))
+    o.unnormalize = int(bool(par.get("UNNORMALIZE", False)))
+    o.norm_factor = float(par.get("norm_factor", 2.0))
+    o.change_metric = int(bool(par.get("CHANGE_METRIC", False)))
+    o.metric_factor = float(par.get("metric_factor", 0.6))
+    o.match_threshold = float(par.get("MatchThreshold", 1.0))          # matchFeatures defaults for non-binary features
+    o.max_ratio = float(par.get("MaxRatio", 0.6))
+    metric = str(par.get("Metric", "SSD")).upper()
+    if metric not in ("SAD", "SSD"):
+        raise ValueError("Metric must be 'SAD' or 'SSD'")
+    o.metric = METRIC_SAD if metric == "SAD" else METRIC_SSD
+    o.unique = int(bool(par.get("Unique", False)))
+    pairs = np.empty((max(n1, 1), 2), dtype=np.int32)
+    mm = np.empty(max(n1, 1), dtype=np.float64)
+    n = C.c_int64()
+    L.check(L.lib().pcreg_get_matches(_ptr(d1, L.c_f64p), n1, max(n1, 1), _ptr(d2, L.c_f64p), n2, max(n2, 1), dim, C.byref(o),
+                                      _ptr(pairs, L.c_i32p), _ptr(mm, L.c_f64p), C.byref(n)), "pcreg_get_matches")
+    pairs = pairs[:n.value].astype(np.int64)
+    return (pairs, mm[:n.value].copy()) if return_metric else pairs
+
+
+def transfer_colors(colored: Model, pts, colors, nn: int = NN_BRUTE):
+    """ColorCodeModel.m:12-18: every point of `pts` takes the colour of its nearest point of the coloured cloud
+    (findNearestNeighbors(pc_col, point, 1) in a loop there; one batched exact 1-NN search here)."""
+    idx, _ = colored.nn_search(pts, nn)
+    return np.asarray(colors)[idx]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -404,7 +449,8 @@ def last_profile() -> dict:
                 grid_nodes_popped=v[9], certified_queries=v[10] - v[23], lazy_skipped_queries=v[23], walked_queries=v[11], rowscan_queries=v[12],
                 list_entries_read=v[13], list_points_gathered=v[14],
                 rowscan_points=v[7], rowscan_rows=v[8], walk_points=v[15], walk_leaves=v[16],
-                list_ms=v[17], rowscan_ms=v[18], walk_ms=v[19], list_launches=v[20], rowscan_launches=v[21], walk_launches=v[22])
+                list_ms=v[17], rowscan_ms=v[18], walk_ms=v[19], list_launches=v[20], rowscan_launches=v[21], walk_launches=v[22],
+                match_score_ms=v[24], match_terms=v[25])
 
 
 def launch_count() -> int:

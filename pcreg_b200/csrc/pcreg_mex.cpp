@@ -25,6 +25,8 @@
 //                                                         counts (Kx1; 0 where the reference returns [])   (getLocalPoints.m)
 //   'spatial_histogram', handle, sample_pts(Kx3 double), options(struct), r_bins, theta_bins, phi_bins
 //                                                      -> feat (Vx3), desc (Vx(nr*nt*np))     (getSpacialHistogramDescriptors.m)
+//   'get_matches', descSurface(N1xD double), descModel(N2xD double), par(struct)
+//                                                      -> matches (Px2 uint32, 1-based), matchMetric (Px1)   (getMatches.m)
 //   'icp', handle, src(Nx3), T0(4x4xH), opts(struct)[, w_src]
 //                                                      -> T(4x4xH), rmse(Hx1), n_used, status, best(1-based), idx(NxH)
 #include <string.h>
@@ -262,6 +264,52 @@ bool cmd_ransac(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], bool
     return true;
 }
 
+bool cmd_get_matches(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 4 || !mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || mxIsComplex(prhs[1]) || mxIsComplex(prhs[2]) || !mxIsStruct(prhs[3]) ||
+        mxGetN(prhs[1]) != mxGetN(prhs[2])) {
+        g_fail = "get_matches: need (descSurface N1xD double, descModel N2xD double, par struct)";
+        return false;
+    }
+    pcreg_match_opts o;
+    pcreg_match_opts_default(&o);
+    o.unnormalize = field_or(prhs[3], "UNNORMALIZE", 0.0) != 0;             // getMatches.m:22
+    o.norm_factor = field_or(prhs[3], "norm_factor", o.norm_factor);
+    o.change_metric = field_or(prhs[3], "CHANGE_METRIC", 0.0) != 0;         // :35
+    o.metric_factor = field_or(prhs[3], "metric_factor", o.metric_factor);
+    o.match_threshold = field_or(prhs[3], "MatchThreshold", 1.0);           // matchFeatures' own defaults when absent
+    o.max_ratio = field_or(prhs[3], "MaxRatio", 0.6);
+    o.unique = field_or(prhs[3], "Unique", 0.0) != 0;
+    o.metric = PCREG_METRIC_SSD;
+    {
+        const mxArray* f = mxGetField(prhs[3], 0, "Metric");
+        char name[16] = "";
+        if (f && mxIsChar(f) && mxGetString(f, name, sizeof name) == 0) {
+            if (!strcmp(name, "SAD") || !strcmp(name, "sad")) o.metric = PCREG_METRIC_SAD;
+            else if (!strcmp(name, "SSD") || !strcmp(name, "ssd")) o.metric = PCREG_METRIC_SSD;
+            else { g_fail = "get_matches: par.Metric must be 'SAD' or 'SSD'"; return false; }
+        }
+    }
+    const int64_t n1 = (int64_t)mxGetM(prhs[1]), n2 = (int64_t)mxGetM(prhs[2]), dim = (int64_t)mxGetN(prhs[1]);
+    int64_t np = 0;
+    int rc;
+    {
+        std::vector<int32_t> pairs((size_t)(n1 > 0 ? n1 : 1) * 2);
+        std::vector<double> mm((size_t)(n1 > 0 ? n1 : 1));
+        rc = pcreg_get_matches(mxGetPr(prhs[1]), n1, n1 > 0 ? n1 : 1, mxGetPr(prhs[2]), n2, n2 > 0 ? n2 : 1, dim, &o, pairs.data(), mm.data(), &np);
+        if (rc == PCREG_OK) {
+            plhs[0] = mxCreateNumericMatrix((mwSize)np, 2, mxUINT32_CLASS, mxREAL);      // indexPairs is uint32 in matchFeatures
+            uint32_t* out = (uint32_t*)mxGetData(plhs[0]);
+            for (int64_t p = 0; p < np; ++p) { out[p] = (uint32_t)pairs[(size_t)(2 * p)] + 1u; out[np + p] = (uint32_t)pairs[(size_t)(2 * p + 1)] + 1u; }
+            if (nlhs > 1) {
+                plhs[1] = mxCreateDoubleMatrix((mwSize)np, 1, mxREAL);
+                for (int64_t p = 0; p < np; ++p) mxGetPr(plhs[1])[p] = mm[(size_t)p];
+            }
+        }
+    }
+    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); return false; }
+    return true;
+}
+
 bool cmd_icp(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     pcreg_model* m = nrhs > 1 ? handle_of(prhs[1]) : nullptr;
     if (!m || nrhs < 5 || !is_pts(prhs[2]) || !mxIsDouble(prhs[3]) || mxGetNumberOfElements(prhs[3]) % 16 != 0) {
@@ -326,6 +374,7 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
         else if (!strcmp(cmd, "estimate_transform")) ok = cmd_estimate_transform(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "ransac")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs, false);
         else if (!strcmp(cmd, "ransac_seeded")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs, true);
+        else if (!strcmp(cmd, "get_matches")) ok = cmd_get_matches(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "icp")) ok = cmd_icp(nlhs, plhs, nrhs, prhs);
         else g_fail = std::string("pcreg_mex: unknown command '") + cmd + "'";
     }

@@ -11,7 +11,7 @@ extern "C" {
 typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef enum { mxUNKNOWN_CLASS = 0, mxLOGICAL_CLASS = 3, mxCHAR_CLASS = 4, mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7,
-               mxINT32_CLASS = 12, mxINT64_CLASS = 14, mxUINT64_CLASS = 15, mxSTRUCT_CLASS = 2 } mxClassID;
+               mxINT32_CLASS = 12, mxUINT32_CLASS = 13, mxINT64_CLASS = 14, mxUINT64_CLASS = 15, mxSTRUCT_CLASS = 2 } mxClassID;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
 mxArray* mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
 mxArray* mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity c);

@@ -46,6 +46,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.AlignOpts) == 48
     assert C.sizeof(_lib.RansacOpts) == 24
     assert C.sizeof(_lib.IcpOpts) == 40
+    assert C.sizeof(_lib.MatchOpts) == 56
 
 
 def test_defaults_are_the_reference_constants(built):
@@ -57,6 +58,10 @@ def test_defaults_are_the_reference_constants(built):
     o = _lib.IcpOpts()
     lib.pcreg_icp_opts_default(C.byref(o))
     assert (o.k_frac, o.R_w, o.reflection_fix) == (0.85, 3.5, 0)
+    mo = _lib.MatchOpts()
+    lib.pcreg_match_opts_default(C.byref(mo))                                   # completeExperiment.m:112-122
+    assert (mo.unnormalize, mo.norm_factor, mo.change_metric, mo.metric_factor) == (1, 2.0, 1, 0.6)
+    assert (mo.match_threshold, mo.max_ratio, mo.metric, mo.unique) == (10.0, 0.99, 0, 1)
 
 
 def test_no_cpu_fallback_without_device(built):

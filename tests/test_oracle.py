@@ -189,3 +189,37 @@ def test_descriptor_is_rotation_invariant_up_to_binning():
     b = oracle.spatial_histogram_of(nb @ Rm, 3.5, K=0.85, ALIGN_POINTS=True)
     assert a.sum() == b.sum() == nb.shape[0]
     assert np.abs(a - b).sum() <= 4
+
+
+def test_getmatches_weighting_and_matchfeatures_semantics():
+    """getMatches.m:22-41 (constant element from the mean 1-norm, element-wise power) and the documented matchFeatures
+    rules on a hand-checkable case: unit-vector normalisation, threshold as a percentage of the largest possible
+    score, nearest / second-nearest ratio, forward-backward uniqueness, first index on ties."""
+    import oracle
+    dS = np.array([[3.0, 0.0, 1.0], [0.0, 2.0, 2.0]])
+    dM = np.array([[0.0, 4.0, 4.0], [6.0, 0.0, 2.0], [1.0, 1.0, 1.0]])
+    par = dict(UNNORMALIZE=True, norm_factor=2, CHANGE_METRIC=True, metric_factor=0.5)
+    wS, wM = oracle.weight_descriptors(dS, dM, par)
+    avg = (4 + 4 + 8 + 8 + 3) / 5.0                                   # mean of the row 1-norms of [dS; dM] (:24)
+    np.testing.assert_allclose(wS, np.sqrt(np.hstack([dS, np.full((2, 1), 2 * avg)])), rtol=1e-15)
+    np.testing.assert_allclose(wM[:, -1], np.sqrt(2 * avg), rtol=1e-15)
+    # scale invariance of the matching itself: dM rows 0 / 1 are dS rows 1 / 0 scaled by 2 -> zero score after normalisation
+    pairs, metric = oracle.match_features_exhaustive(dS, dM, oracle.matching.SAD, 10.0, 0.99, True)
+    assert pairs.tolist() == [[0, 1], [1, 0]] and np.all(metric < 1e-15)
+    # MatchThreshold: 10 % of 2*sqrt(3) = 0.346; a row at SAD distance > that from everything is dropped
+    far = np.array([[0.0, 1.0, 0.0]])
+    p2, m2 = oracle.match_features_exhaustive(far, dM, oracle.matching.SAD, 10.0, 1.0, False)
+    assert p2.shape == (0, 2)
+    p3, m3 = oracle.match_features_exhaustive(far, dM, oracle.matching.SAD, 100.0, 1.0, False)
+    assert p3.tolist() == [[0, 0]] and abs(m3[0] - (1 - 1 / np.sqrt(2) + 1 / np.sqrt(2))) < 1e-15
+    # MaxRatio: two equally near model rows -> ratio 1 -> dropped at 0.99, kept (first index) at 1.0
+    twin = np.vstack([dM[2], dM[2], dM[0]])
+    assert oracle.match_features_exhaustive(dS[:1], twin, oracle.matching.SAD, 100.0, 0.99, False)[0].shape == (0, 2)
+    assert oracle.match_features_exhaustive(dS[:1], twin, oracle.matching.SAD, 100.0, 1.0, False)[0].tolist() == [[0, 0]]
+    # Unique: two identical surface rows compete for one model row, the first keeps it
+    both = np.vstack([dS[0], dS[0]])
+    pu, _ = oracle.match_features_exhaustive(both, dM, oracle.matching.SAD, 100.0, 1.0, True)
+    assert pu.tolist() == [[0, 1]]
+    # SSD: largest possible score 4
+    ps, ms = oracle.match_features_exhaustive(dS, -dS, oracle.matching.SSD, 100.0, 1.0, False)
+    assert ps.shape[0] == 2 and np.all(ms <= 4.0 + 1e-12)
