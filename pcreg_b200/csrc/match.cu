@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(MTHREADS) k_match_scores(const __grid_constant
         for (int k = 0; k < MK; ++k) {
             const double2 a01 = *reinterpret_cast<const double2*>(&As[buf][k][ty * 4]);
             const double2 a23 = *reinterpret_cast<const double2*>(&As[buf][k][ty * 4 + 2]);
-            const double2 b01 = *reinterpret_cast<const double2*>(&Bs[buf][k][tx * 4]);
-            const double2 b23 = *reinterpret_cast<const double2*>(&Bs[buf][k][tx * 4 + 2]);
+            // columns {2tx, 2tx+1, 32+2tx, 32+2tx+1}: the 16 lanes of a half warp read 256 contiguous bytes per load
+            // (a 32-byte stride would put lanes t and t+4 on the same banks)
+            const double2 b01 = *reinterpret_cast<const double2*>(&Bs[buf][k][tx * 2]);
+            const double2 b23 = *reinterpret_cast<const double2*>(&Bs[buf][k][32 + tx * 2]);
             const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -101,17 +103,20 @@ __global__ void __launch_bounds__(MTHREADS) k_match_scores(const __grid_constant
 
     // ---- epilogue: the tile never reaches memory ----
     const double INF = INFINITY;
+    int colof[4];                                            // tile column of acc[.][j], ascending in j
+#pragma unroll
+    for (int j = 0; j < 4; ++j) colof[j] = tx * 2 + (j & 1) + (j >> 1) * 32;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (r0 + ty * 4 + i >= a.n1 || c0 + tx * 4 + j >= a.n2) acc[i][j] = INF;       // padding rows / columns never win
+            if (r0 + ty * 4 + i >= a.n1 || c0 + colof[j] >= a.n2) acc[i][j] = INF;       // padding rows / columns never win
     // rows: nearest / second nearest model descriptor among this tile's 64 columns
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         Top2 t{INF, INF, INT_MAX};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) top2_merge(t, acc[i][j], INF, (int)(c0 + tx * 4 + j));
+        for (int j = 0; j < 4; ++j) top2_merge(t, acc[i][j], INF, (int)(c0 + colof[j]));
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {                    // the 16 threads of a row group are one half warp
             const double od1 = __shfl_xor_sync(0xffffffffu, t.d1, o), od2 = __shfl_xor_sync(0xffffffffu, t.d2, o);
@@ -132,8 +137,8 @@ __global__ void __launch_bounds__(MTHREADS) k_match_scores(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (acc[i][j] < d) { d = acc[i][j]; bi = (int)(r0 + ty * 4 + i); }
-        cs_d[ty * MT + tx * 4 + j] = d;
-        cs_i[ty * MT + tx * 4 + j] = bi;
+        cs_d[ty * MT + colof[j]] = d;
+        cs_i[ty * MT + colof[j]] = bi;
     }
     __syncthreads();
     if (tid < MT) {
