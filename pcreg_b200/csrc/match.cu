@@ -46,7 +46,7 @@ __device__ __forceinline__ void top2_merge(Top2& a, double bd1, double bd2, int 
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(MTHREADS) k_match_scores(const __grid_constant__ MatchArgs a) {
+__global__ void __launch_bounds__(MTHREADS, 3) k_match_scores(const __grid_constant__ MatchArgs a) {
     __shared__ __align__(16) double As[2][MK][MT];
     __shared__ __align__(16) double Bs[2][MK][MT];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
