@@ -350,6 +350,42 @@ def roofline_for(w, r):
                 note="6 FLOP per (query, model point) pair; includes the bound pass and the FP64 slow path in the time")
 
 
+FP64_INST_PEAK_MEASURED = 16.45e12    # DFMA issue rate, tools/fma_peak.cu (32.9 TFLOP/s; profiles/r01_fma_peak.txt)
+
+
+def match_workload(P, torch, n1=3000, n2=20000, dim=980, reps=3):
+    """SURVEY.md section 8 row f4 beside the headline: getMatches (descriptor weighting + exhaustive matchFeatures) of n1 surface
+    against n2 model descriptors through the host-buffer API.  The score kernel is FP64-pipe bound: 2 FP64 instructions
+    per (pair, dimension) term for SAD."""
+    g = np.random.default_rng(1)
+    dS = g.poisson(g.gamma(0.6, 4.0, (n1, dim))).astype(np.float64)
+    dM = g.poisson(g.gamma(0.6, 4.0, (n2, dim))).astype(np.float64)
+    dM[::7][: n1 // 2] = dS[: n1 // 2]                                             # some exact partners, so matches exist
+    par = dict(UNNORMALIZE=True, norm_factor=2, CHANGE_METRIC=True, metric_factor=0.6, MatchThreshold=10, MaxRatio=0.99,
+               Metric="SAD", Unique=True)                                          # completeExperiment.m:112-122
+    dS, dM = np.asfortranarray(dS), np.asfortranarray(dM)
+    P.getMatches(dS[:64], dM[:64], par)
+    launches0 = P.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        matches = P.getMatches(dS, dM, par)
+    wall_ms = (time.perf_counter() - t0) * 1e3 / reps
+    launches = (P.launch_count() - launches0) // reps
+    P.set_profiling(True)
+    P.getMatches(dS, dM, par)
+    pr = P.last_profile()
+    P.set_profiling(False)
+    inst_s = 2.0 * pr["match_terms"] / (pr["match_score_ms"] * 1e-3)
+    return dict(workload="getMatches: %d surface x %d model descriptors, 981 dimensions, SAD, exhaustive matchFeatures" % (n1, n2),
+                value=n1 * n2 / (wall_ms * 1e-3), unit="descriptor pairs/s (host buffers, H2D inside)", ms_per_call=wall_ms,
+                h2d_bytes_per_call=int(dS.nbytes + dM.nbytes), matches=int(matches.shape[0]), gpu_launches=int(launches),
+                roofline=dict(bound="fp64_pipe", kernel="k_match_scores", achieved=inst_s / 1e12, peak=FP64_INST_PEAK_MEASURED / 1e12,
+                              unit="T FP64 inst/s", frac=inst_s / FP64_INST_PEAK_MEASURED, avg_launch_ms=pr["match_score_ms"],
+                              terms_per_launch=pr["match_terms"],
+                              note="2 FP64 instructions per (pair, dimension) term (t = a - b; acc += |t|); peak = measured DFMA issue rate"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -359,6 +395,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-c2", action="store_true", help="skip the secondary C2 (brute-force) measurement at N=1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-match", action="store_true", help="skip the getMatches (row f4) side measurement at N=1")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -411,6 +448,8 @@ def main():
         line["c2"]["grid_path"] = dict(workload=w3["desc"], value=r3["q_per_step"] / (r3["ms_per_step"] * 1e-3), unit="queries/s",
                                        ms_per_step=r3["ms_per_step"], e2e_ms_per_step=r3["ms_per_step_e2e"], best_rmse=r3["rmse_best"],
                                        same_result_as_brute=bool(r3["rmse_best"] == r2["rmse_best"]))
+    if rank == 0 and world == 1 and not args.no_match and args.workload == "c3":
+        line["get_matches"] = match_workload(P, torch)
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         c = cpu_sample(w, budget_s=15.0)

@@ -267,8 +267,8 @@ int pcreg_get_matches(const double* desc_surface, int64_t n1, int64_t ld1, const
     DevBuf<double> A((size_t)kdim * n1p), B((size_t)kdim * n2p), l1((size_t)(n1 + n2)), avg(1);
     PCREG_CUDA(cudaMemsetAsync(A.p, 0, A.bytes(), st));
     PCREG_CUDA(cudaMemsetAsync(B.p, 0, B.bytes(), st));
-    PCREG_CUDA(cudaMemcpy2DAsync(A.p, (size_t)n1p * 8, desc_surface, (size_t)ld1 * 8, (size_t)n1 * 8, (size_t)dim, cudaMemcpyHostToDevice, st));
-    PCREG_CUDA(cudaMemcpy2DAsync(B.p, (size_t)n2p * 8, desc_model, (size_t)ld2 * 8, (size_t)n2 * 8, (size_t)dim, cudaMemcpyHostToDevice, st));
+    h2d_columns(A.p, n1p, desc_surface, ld1, n1, dim, st);           // pageable MATLAB / numpy memory -> pinned bounce buffers -> device
+    h2d_columns(B.p, n2p, desc_model, ld2, n2, dim, st);
     const unsigned g1 = (unsigned)((n1 + 127) / 128), g2 = (unsigned)((n2 + 127) / 128);
     if (opts->unnormalize) {
         k_match_l1<<<g1, 128, 0, st>>>(A.p, n1, n1p, (int)dim, l1.p);

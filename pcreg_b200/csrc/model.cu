@@ -105,6 +105,39 @@ cudaStream_t lane_stream(int i) {
     return c.streams[i];
 }
 Context& ctx() { return g_ctx; }
+
+constexpr size_t PINNED_BYTES = (size_t)16 << 20;
+void h2d_columns(double* d_dst, int64_t ld_dst, const double* h_src, int64_t ld_src, int64_t rows, int64_t ncols, cudaStream_t st) {
+    if (rows <= 0 || ncols <= 0) return;
+    Context& c = g_ctx;
+    for (int b = 0; b < 2; ++b) {
+        if (!c.pinned[b]) {
+            PCREG_CUDA(cudaHostAlloc(&c.pinned[b], PINNED_BYTES, cudaHostAllocDefault));
+            PCREG_CUDA(cudaEventCreateWithFlags(&c.pinned_ev[b], cudaEventDisableTiming));
+        }
+    }
+    const size_t col_bytes = (size_t)rows * sizeof(double);
+    if (col_bytes > PINNED_BYTES) {           // a single column larger than a bounce buffer: let the runtime stage it
+        PCREG_CUDA(cudaMemcpy2DAsync(d_dst, (size_t)ld_dst * 8, h_src, (size_t)ld_src * 8, col_bytes, (size_t)ncols, cudaMemcpyHostToDevice, st));
+        return;
+    }
+    const int64_t per = (int64_t)(PINNED_BYTES / col_bytes);
+    int b = 0;
+    bool used[2] = {false, false};
+    for (int64_t c0 = 0; c0 < ncols; c0 += per, b ^= 1) {
+        const int64_t nc = std::min<int64_t>(per, ncols - c0);
+        if (used[b]) PCREG_CUDA(cudaEventSynchronize(c.pinned_ev[b]));          // the DMA that read this buffer has finished
+        char* stage = (char*)c.pinned[b];
+        if (ld_src == rows) memcpy(stage, h_src + c0 * ld_src, (size_t)nc * col_bytes);
+        else for (int64_t k = 0; k < nc; ++k) memcpy(stage + (size_t)k * col_bytes, h_src + (c0 + k) * ld_src, col_bytes);
+        PCREG_CUDA(cudaMemcpy2DAsync(d_dst + c0 * ld_dst, (size_t)ld_dst * 8, stage, col_bytes, col_bytes, (size_t)nc, cudaMemcpyHostToDevice, st));
+        PCREG_CUDA(cudaEventRecord(c.pinned_ev[b], st));
+        used[b] = true;
+    }
+    // the caller may reuse / free h_src right away (it was copied), but the bounce buffers are still being read:
+    // the next h2d_columns call waits on its own events only if it reuses them, so drain here to keep it simple
+    for (int k = 0; k < 2; ++k) if (used[k]) PCREG_CUDA(cudaEventSynchronize(c.pinned_ev[k]));
+}
 void require_init() {
     if (!g_ctx.initialised) throw ArgError{"pcreg_init has not been called (or failed): no CUDA device, and there is no CPU fallback"};
 }
@@ -390,6 +423,10 @@ int pcreg_shutdown(void) {
         cudaDeviceSynchronize();
         for (cudaEvent_t e : ctx().events) cudaEventDestroy(e);
         ctx().events.clear();
+        for (int b = 0; b < 2; ++b) {
+            if (ctx().pinned[b]) { cudaFreeHost(ctx().pinned[b]); ctx().pinned[b] = nullptr; }
+            if (ctx().pinned_ev[b]) { cudaEventDestroy(ctx().pinned_ev[b]); ctx().pinned_ev[b] = nullptr; }
+        }
         pool_trim(0);
     }
     ctx().initialised = false;

@@ -58,6 +58,8 @@ struct Context {
     double profile[32] = {0};
     std::vector<cudaEvent_t> events;     // reusable timing events (profiling mode)
     std::vector<cudaStream_t> streams;   // internal streams of the two-lane ICP loop
+    void* pinned[2] = {nullptr, nullptr};   // bounce buffers of h2d_columns (allocated on first use)
+    cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
 };
 cudaEvent_t pooled_event(size_t i);      // i-th reusable event, created on first use
 cudaStream_t lane_stream(int i);         // i-th internal stream (non-blocking), created on first use
@@ -221,6 +223,11 @@ void local_points_device(const pcreg_model* m, const double* centres, int64_t nc
                          int64_t max_points, LocalPointsDev& out, cudaStream_t st);
 
 void grid_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st);
+// Upload of a column-major host matrix (ncols columns of `rows` doubles, column stride ld_src) from PAGEABLE memory
+// into a device matrix with column stride ld_dst: columns are packed into two alternating pinned bounce buffers and
+// sent asynchronously, so the host-side packing of one chunk overlaps the DMA of the previous one (a plain
+// cudaMemcpy2D from pageable memory stages row by row at ~2 GB/s).  Returns after the last chunk is queued on st.
+void h2d_columns(double* d_dst, int64_t ld_dst, const double* h_src, int64_t ld_src, int64_t rows, int64_t ncols, cudaStream_t st);
 // MATLAB column-major 4x4 <-> internal row-major 4x4, batched (a transpose either way)
 void transpose16_launch(const double* d_in, double* d_out, int64_t n, cudaStream_t st);
 
