@@ -395,7 +395,10 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     // lane so that the per-kernel event times stay meaningful.  PCREG_LANES=1 disables.
     const char* lanes_e = getenv("PCREG_LANES");                            // 1 = off, 2 = on whatever the batch size (tests)
     const int lanes_env = lanes_e ? atoi(lanes_e) : 0;
-    const int nlanes = (prof || lanes_env == 1 || nhyp < 2 || (lanes_env != 2 && (double)nhyp * (double)ns < 2.0e6)) ? 1 : 2;
+    constexpr int MAX_LANES = 4;
+    const int lanes_want = lanes_env > 2 ? std::min(lanes_env, MAX_LANES) : 2;
+    const int nlanes = (prof || lanes_env == 1 || nhyp < 2 || (lanes_env < 2 && (double)nhyp * (double)ns < 2.0e6)) ? 1
+                       : (int)std::min<int64_t>(lanes_want, nhyp);
     int64_t hc = (int64_t)std::max<size_t>(1, budget / (per_hyp * (size_t)nlanes));
     if (const char* e = getenv("PCREG_MAX_CHUNK_HYP")) { const long v = atol(e); if (v > 0) hc = std::min<int64_t>(hc, v); }   // tests: force several chunks
     hc = std::min(hc, (nhyp + nlanes - 1) / nlanes);
@@ -435,7 +438,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         bool have_prev = false;
         int64_t h0 = 0, hn = 0;
     };
-    Lane lanes[2];
+    Lane lanes[MAX_LANES];
     for (int l = 0; l < nlanes; ++l) {
         Lane& L = lanes[l];
         L.st = (nlanes == 1) ? st : lane_stream(l);
