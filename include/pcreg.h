@@ -196,6 +196,22 @@ int  pcreg_ransac_run(const double* p1, const double* p2, int64_t P, int64_t ld,
                       const pcreg_ransac_opts* opts, double* T16_best, int32_t* inl_idx, int64_t* n_inl,
                       int64_t* n_succ, int64_t* max_inl, int64_t* best_hyp, int32_t* triplets_out);
 
+/* ransac.m:21-116 for a BATCH of windows in one call -- the reference runs one ransac per matching window under
+ * parfor (slideMatchingWindow_v2.m:178-198: 21 windows per experiment, completeExperiment.m:265-278); here all
+ * windows x iter_num hypotheses are one launch.  p1, p2: ntotal x 3 column-major doubles (ld); window w = rows
+ * offsets[w] .. offsets[w+1]-1 (P_w pairs, thInlr = round(thInlrRatio * P_w) per window).
+ * Samples: triplets != NULL -> [nwin][iter_num][3], 0-based RELATIVE to the window; else window w draws
+ * iter_num samples with pcreg_ransac_run's sampler from seeds[w].
+ * Outputs per window: T16 [nwin][16] (NaN where the reference returns []), inl_idx [ntotal] (window w's inliers,
+ * 0-based relative to the window, ascending, in inl_idx[offsets[w] .. offsets[w]+n_inl[w]-1]), n_inl, n_succ,
+ * max_inl, best_hyp (-1 = none), status [nwin]: 0 ok, 1 = T = [] (ransac.m:75-89; also a window with fewer than
+ * 3 pairs, where the reference's randperm(ptNum)(1:3) would throw).  Each window's result equals a
+ * pcreg_ransac_run / pcreg_ransac_score call on that window alone. */
+int  pcreg_ransac_batch(const double* p1, const double* p2, int64_t ld, const int64_t* offsets, int64_t nwin,
+                        int64_t iter_num, const int32_t* triplets, const uint64_t* seeds,
+                        const pcreg_ransac_opts* opts, double* T16, int32_t* inl_idx, int64_t* n_inl,
+                        int64_t* n_succ, int64_t* max_inl, int64_t* best_hyp, int32_t* status);
+
 /* ---- batched ICP (composition of quickTF.m, the 85 % trim rule AlignPoints_KNN.m:20-26, the
  *      weights of AlignPoints_weighted.m:16-18, estimateTransform.m:41-71 and ransac.m's
  *      score / first-arg-best structure around an exact NN step) --------- */

@@ -79,6 +79,8 @@ SIGNATURES = {
                                      c_f64p, c_i32p, c_i64p, c_i64p, c_i64p, c_i64p, c_i32p, c_i32p, c_f64p]),
     "pcreg_ransac_run": (C.c_int, [c_f64p, c_f64p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.POINTER(RansacOpts),
                                    c_f64p, c_i32p, c_i64p, c_i64p, c_i64p, c_i64p, c_i32p]),
+    "pcreg_ransac_batch": (C.c_int, [c_f64p, c_f64p, C.c_int64, c_i64p, C.c_int64, C.c_int64, c_i32p, C.POINTER(C.c_uint64),
+                                     C.POINTER(RansacOpts), c_f64p, c_i32p, c_i64p, c_i64p, c_i64p, c_i64p, c_i32p]),
     "pcreg_icp_opts_default": (None, [C.POINTER(IcpOpts)]),
     "pcreg_icp_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, c_f64p, c_f64p, C.c_int64,
                                   C.POINTER(IcpOpts), c_f64p, c_f64p, c_i32p, c_i32p, c_i32p, c_f64p, c_i64p]),

@@ -400,6 +400,51 @@ def ransac_seeded(pts1, pts2, coef: dict, seed: int = 0, reflection_fix=False, r
     return out
 
 
+def ransac_batch(pts1_list, pts2_list, coef: dict, seeds=None, triplets_list=None, reflection_fix=False):
+    """ransac.m for a batch of matching windows in ONE call (the reference runs one `ransac` per window under parfor:
+    slideMatchingWindow_v2.m:178-198).  Window w is (pts1_list[w], pts2_list[w]).  Samples: `triplets_list[w]`
+    (0-based [iterNum, 3], the same iterNum for every window) or, when None, drawn on the device from `seeds[w]`
+    (default seeds = 0..nwin-1) by the sampler of ransac_seeded().  Returns one dict per window with the reference's
+    five outputs; T is None where the reference returns [] (also for windows with fewer than 3 pairs)."""
+    nw = len(pts1_list)
+    sizes = np.array([np.asarray(p).reshape(-1, 3).shape[0] for p in pts1_list], dtype=np.int64)
+    offsets = np.zeros(nw + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    nt = int(offsets[-1])
+    p1 = np.asfortranarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in pts1_list], axis=0))
+    p2 = np.asfortranarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in pts2_list], axis=0))
+    if p1.shape != p2.shape:
+        raise ValueError("pts1 and pts2 must have the same shapes")
+    tri = sd = None
+    if triplets_list is not None:
+        tri = np.ascontiguousarray(np.stack([np.asarray(t, dtype=np.int32).reshape(-1, 3) for t in triplets_list], axis=0))
+        nh = tri.shape[1]
+    else:
+        nh = int(coef["iterNum"])
+        sd = np.array([int(x) & (2 ** 64 - 1) for x in (range(nw) if seeds is None else seeds)], dtype=np.uint64)
+        if sd.shape != (nw,):
+            raise ValueError("one seed per window")
+    o = RansacOpts(float(coef["thDist"]), float(coef["thInlrRatio"]), int(bool(coef.get("REFINE", True))), int(bool(reflection_fix)))
+    T = np.empty((nw, 16), dtype=np.float64)
+    inl = np.empty(max(nt, 1), dtype=np.int32)
+    n_inl, n_succ, max_inl, best = (np.empty(nw, dtype=np.int64) for _ in range(4))
+    st = np.empty(nw, dtype=np.int32)
+    L.check(L.lib().pcreg_ransac_batch(_ptr(p1, L.c_f64p), _ptr(p2, L.c_f64p), max(nt, 1), _ptr(offsets, L.c_i64p), nw, nh,
+                                       _ptr(tri, L.c_i32p), _ptr(sd, C.POINTER(C.c_uint64)), C.byref(o), _ptr(T, L.c_f64p),
+                                       _ptr(inl, L.c_i32p), _ptr(n_inl, L.c_i64p), _ptr(n_succ, L.c_i64p), _ptr(max_inl, L.c_i64p),
+                                       _ptr(best, L.c_i64p), _ptr(st, L.c_i32p)), "pcreg_ransac_batch")
+    Ts = _T_from_abi(T, nw)
+    out = []
+    for w in range(nw):
+        if st[w] != 0:
+            out.append(dict(T=None, inlierIdx=np.zeros(0, dtype=np.int64), numSuccess=0, maxInliers=0, pct=0.0, best=-1))
+        else:
+            a = int(offsets[w])
+            out.append(dict(T=Ts[w], inlierIdx=inl[a:a + int(n_inl[w])].astype(np.int64), numSuccess=int(n_succ[w]),
+                            maxInliers=int(max_inl[w]), pct=100.0 * int(max_inl[w]) / int(sizes[w]), best=int(best[w])))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # batched ICP
 # ------------------------------------------------------------------------------------------------

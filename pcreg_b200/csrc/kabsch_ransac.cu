@@ -1,6 +1,7 @@
 // kabsch_ransac.cu -- batched estimateTransform (estimateTransform.m:2-74) and the hypothesis
 // scoring loop of ransac.m:40-73, one warp per hypothesis, sample triplets supplied by the host.
 #include <math.h>
+#include <stdio.h>
 #include <float.h>
 #include <algorithm>
 #include <vector>
@@ -167,13 +168,18 @@ struct RansacArgs {
     const int32_t* triplets; int64_t nhyp;
     double thDist; double thInlr; int refine; int reflection_fix;
     int32_t* cnt; int32_t* cnt_ref; double* T_rm;      // [nhyp], [nhyp], [nhyp][16] (NaN where no TForm kept)
+    // batch of windows (pcreg_ransac_batch): hypothesis h belongs to window h / hyp_per_win, whose pairs are rows
+    // win_off[w] .. win_off[w+1]-1; triplets are relative to the window; thInlr = round(ratio * P_w) per window
+    const int64_t* win_off; int64_t hyp_per_win; double ratio;
 };
+// the pairs one hypothesis is scored on
+struct RansacView { const double* p1; const double* p2; int64_t P; int64_t ld; double thDist; double thInlr; };
 
 __device__ __forceinline__ void load_pt(const double* __restrict__ p, int64_t ld, int64_t i, double* o) {
     o[0] = p[i]; o[1] = p[ld + i]; o[2] = p[2 * ld + i];
 }
 
-__device__ __forceinline__ int warp_count_inliers(const RansacArgs& a, const double* T, int lane) {
+__device__ __forceinline__ int warp_count_inliers(const RansacView& a, const double* T, int lane) {
     int c = 0;
     for (int64_t i = lane; i < a.P; i += 32) {
         double x[3], y[3], qx, qy, qz;
@@ -185,20 +191,31 @@ __device__ __forceinline__ int warp_count_inliers(const RansacArgs& a, const dou
     return warp_sum_i(c);
 }
 
-__global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ RansacArgs a) {
+__global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ RansacArgs g) {
     const int lane = threadIdx.x & 31;
     const int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (h >= a.nhyp) return;
+    if (h >= g.nhyp) return;
+    int64_t row0 = 0, np_win = g.P;
+    double th_win = g.thInlr;
+    if (g.win_off) {
+        const int64_t w = h / g.hyp_per_win;
+        row0 = g.win_off[w];
+        np_win = g.win_off[w + 1] - row0;
+        th_win = floor(g.ratio * (double)np_win + 0.5);                         // MATLAB round, ransac.m:28
+    }
+    // (the view is built once from values: patching the pointers of a copy of the __grid_constant__ struct in place was
+    // miscompiled by nvcc 12.9 -- the pointer increments were dropped)
+    const RansacView a{g.p1 + row0, g.p2 + row0, np_win, g.ld, g.thDist, th_win};
     const double nanv = nan("");
     double T1[16];
     int st = 1;
     int32_t s3[3];
-    for (int k = 0; k < 3; ++k) s3[k] = a.triplets[h * 3 + k];
-    const bool valid = s3[0] >= 0 && s3[1] >= 0 && s3[2] >= 0 && s3[0] < a.P && s3[1] < a.P && s3[2] < a.P;
+    for (int k = 0; k < 3; ++k) s3[k] = g.triplets[h * 3 + k];
+    const bool valid = a.P >= 3 && s3[0] >= 0 && s3[1] >= 0 && s3[2] >= 0 && s3[0] < a.P && s3[1] < a.P && s3[2] < a.P;
     if (valid) {
         double P1[9], P2[9];
         for (int i = 0; i < 3; ++i) { load_pt(a.p1, a.ld, s3[i], P1 + 3 * i); load_pt(a.p2, a.ld, s3[i], P2 + 3 * i); }
-        st = kabsch3(P1, P2, a.reflection_fix != 0, T1);                        // ransac.m:45
+        st = kabsch3(P1, P2, g.reflection_fix != 0, T1);                        // ransac.m:45
     }
     int cnt = 0, cnt_ref = 0;
     bool keep = false;
@@ -206,7 +223,7 @@ __global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ Ra
     if (st == 0) {
         cnt = warp_count_inliers(a, T1, lane);                                  // ransac.m:48-50
         if ((double)cnt >= a.thInlr) {                                          // :53
-            if (a.refine) {
+            if (g.refine) {
                 // refit on the inliers (:55): pivots = first sample point of each set
                 double piv1[3], piv2[3];
                 load_pt(a.p1, a.ld, s3[0], piv1);
@@ -226,7 +243,7 @@ __global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ Ra
                     }
                     double P1[9], P2[9];
                     for (int i = 0; i < 3; ++i) { load_pt(a.p1, a.ld, id[i], P1 + 3 * i); load_pt(a.p2, a.ld, id[i], P2 + 3 * i); }
-                    st2 = kabsch3(P1, P2, a.reflection_fix != 0, T2);
+                    st2 = kabsch3(P1, P2, g.reflection_fix != 0, T2);
                 } else {
                     double s[NS_FIT];
 #pragma unroll
@@ -240,7 +257,7 @@ __global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ Ra
                     }
 #pragma unroll
                     for (int k = 0; k < NS_FIT; ++k) s[k] = warp_sum(s[k]);
-                    st2 = fit_from_sums(s, cnt, piv1, piv2, a.reflection_fix != 0, T2);
+                    st2 = fit_from_sums(s, cnt, piv1, piv2, g.reflection_fix != 0, T2);
                 }
                 if (st2 == 0) {
                     cnt_ref = warp_count_inliers(a, T2, lane);                  // :56-58
@@ -256,10 +273,10 @@ __global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ Ra
         }
     }
     if (lane == 0) {
-        a.cnt[h] = cnt;
-        a.cnt_ref[h] = cnt_ref;
+        g.cnt[h] = cnt;
+        g.cnt_ref[h] = cnt_ref;
     }
-    if (lane < 16) a.T_rm[h * 16 + lane] = keep ? Tk[lane] : nanv;
+    if (lane < 16) g.T_rm[h * 16 + lane] = keep ? Tk[lane] : nanv;
 }
 
 // inlier flags of one transform (final calcDists, ransac.m:78,92)
@@ -300,6 +317,100 @@ __global__ void k_gen_triplets(unsigned long long seed, int64_t nhyp, int64_t P,
     if (i2 >= lo) ++i2;
     if (i2 >= hi) ++i2;
     tri[3 * h + 0] = (int32_t)i0; tri[3 * h + 1] = (int32_t)i1; tri[3 * h + 2] = (int32_t)i2;
+}
+
+// ---- batch of windows (pcreg_ransac_batch) ---------------------------------------------------------------
+// The same sampler per window: window w draws from seeds[w] over its own P_w pairs (indices relative to the window).
+__device__ __forceinline__ void draw_triplet(unsigned long long seed, int64_t h, int64_t P, int32_t* t) {
+    const unsigned long long u0 = splitmix64(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(3 * h + 1));
+    const unsigned long long u1 = splitmix64(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(3 * h + 2));
+    const unsigned long long u2 = splitmix64(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(3 * h + 3));
+    const long long i0 = (long long)(u0 % (unsigned long long)P);
+    long long i1 = (long long)(u1 % (unsigned long long)(P - 1));
+    if (i1 >= i0) ++i1;
+    long long i2 = (long long)(u2 % (unsigned long long)(P - 2));
+    const long long lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+    if (i2 >= lo) ++i2;
+    if (i2 >= hi) ++i2;
+    t[0] = (int32_t)i0; t[1] = (int32_t)i1; t[2] = (int32_t)i2;
+}
+__global__ void k_gen_triplets_batch(const unsigned long long* __restrict__ seeds, const int64_t* __restrict__ win_off,
+                                     int64_t nwin, int64_t iter_num, int32_t* __restrict__ tri) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nwin * iter_num) return;
+    const int64_t w = g / iter_num, h = g - w * iter_num, P = win_off[w + 1] - win_off[w];
+    int32_t t[3] = {-1, -1, -1};                        // fewer than 3 pairs: no sample (the window reports [])
+    if (P >= 3) draw_triplet(seeds[w], h, P, t);
+    tri[3 * g + 0] = t[0]; tri[3 * g + 1] = t[1]; tri[3 * g + 2] = t[2];
+}
+
+// One block per window: first arg-max of the deciding counts (ransac.m:69-73), numSuccess (ransac.m:94-98), the
+// winner's transform (row-major -> the ABI's column-major) and the window's status (1 = ransac.m:75-89 returns []).
+__global__ void __launch_bounds__(256) k_ransac_pick(const int32_t* __restrict__ dec, const double* __restrict__ T_rm,
+                                                     const int64_t* __restrict__ win_off, int64_t iter_num, double ratio,
+                                                     double* __restrict__ T_best_cm, int64_t* __restrict__ best_hyp,
+                                                     int64_t* __restrict__ max_inl, int64_t* __restrict__ n_succ,
+                                                     int32_t* __restrict__ status) {
+    __shared__ int s_cnt[256];
+    __shared__ long long s_idx[256];
+    __shared__ long long s_succ[256];
+    const int64_t w = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t P = win_off[w + 1] - win_off[w];
+    const double thInlr = floor(ratio * (double)P + 0.5);
+    const int32_t* d = dec + w * iter_num;
+    int bc = -1; long long bi = 0, ns = 0;
+    for (int64_t h = tid; h < iter_num; h += 256) {      // ascending h per thread: '>' keeps the first maximum
+        const int c = d[h];
+        if (c > bc) { bc = c; bi = h; }
+        ns += ((double)c >= thInlr) ? 1 : 0;
+    }
+    s_cnt[tid] = bc; s_idx[tid] = bi; s_succ[tid] = ns;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+            const int c2 = s_cnt[tid + o]; const long long i2 = s_idx[tid + o];
+            if (c2 > s_cnt[tid] || (c2 == s_cnt[tid] && c2 >= 0 && i2 < s_idx[tid])) { s_cnt[tid] = c2; s_idx[tid] = i2; }
+            s_succ[tid] += s_succ[tid + o];
+        }
+        __syncthreads();
+    }
+    const long long b = s_idx[0];
+    const double* Tb = T_rm + (w * iter_num + b) * 16;
+    const bool ok = (Tb[0] == Tb[0]);                    // NaN: no TForm kept at the arg-max
+    if (tid < 16) {
+        const int r = tid >> 2, c = tid & 3;
+        T_best_cm[w * 16 + c * 4 + r] = ok ? Tb[tid] : nan("");
+    }
+    if (tid == 0) {
+        status[w] = ok ? 0 : 1;
+        best_hyp[w] = ok ? b : -1;
+        max_inl[w] = ok ? (int64_t)s_cnt[0] : 0;
+        n_succ[w] = ok ? s_succ[0] : 0;
+    }
+}
+
+// final calcDists of every window with its winner (ransac.m:78,92): one thread per pair, window by binary search
+__global__ void k_inlier_flags_batch(const double* __restrict__ p1, const double* __restrict__ p2, int64_t ntotal, int64_t ld,
+                                     const int64_t* __restrict__ win_off, int64_t nwin, const double* __restrict__ T_rm,
+                                     const int64_t* __restrict__ best_hyp, int64_t iter_num, double thDist,
+                                     uint8_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntotal) return;
+    int64_t lo = 0, hi = nwin;                           // largest w with win_off[w] <= i (empty windows skipped by '<=')
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (win_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int64_t b = best_hyp[lo];
+    uint8_t f = 0;
+    if (b >= 0) {
+        const double* T = T_rm + (lo * iter_num + b) * 16;
+        double qx, qy, qz;
+        quick_tf(T, p2[i], p2[ld + i], p2[2 * ld + i], qx, qy, qz);
+        f = dist2_exact(p1[i], p1[ld + i], p1[2 * ld + i], qx, qy, qz) < thDist ? 1 : 0;
+    }
+    flags[i] = f;
 }
 
 }  // namespace pcreg
@@ -429,6 +540,74 @@ int pcreg_ransac_run(const double* p1, const double* p2, int64_t P, int64_t ld, 
     if (triplets_out) PCREG_CUDA(cudaMemcpyAsync(triplets_out, dtri.p, dtri.bytes(), cudaMemcpyDeviceToHost, st));
     return ransac_core(p1, p2, P, ld, dtri.p, iter_num, opts, T16_best, inl_idx, n_inl, n_succ, max_inl, best_hyp, nullptr, nullptr,
                        nullptr, st);
+    PCREG_API_END
+}
+
+int pcreg_ransac_batch(const double* p1, const double* p2, int64_t ld, const int64_t* offsets, int64_t nwin, int64_t iter_num,
+                       const int32_t* triplets, const uint64_t* seeds, const pcreg_ransac_opts* opts, double* T16,
+                       int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ, int64_t* max_inl, int64_t* best_hyp, int32_t* status) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(p1 && p2 && offsets && opts && T16 && inl_idx && n_inl && n_succ && max_inl && best_hyp && status,
+                  "pcreg_ransac_batch: null pointer");
+    PCREG_REQUIRE(triplets || seeds, "pcreg_ransac_batch: need triplets or seeds");
+    PCREG_REQUIRE(nwin >= 1 && iter_num >= 1, "pcreg_ransac_batch: need nwin >= 1 and iter_num >= 1");
+    const int64_t ntotal = offsets[nwin];
+    PCREG_REQUIRE(offsets[0] == 0 && ntotal >= 0 && ld >= ntotal, "pcreg_ransac_batch: bad offsets / ld");
+    for (int64_t w = 0; w < nwin; ++w) PCREG_REQUIRE(offsets[w + 1] >= offsets[w], "pcreg_ransac_batch: offsets must be non-decreasing");
+    const int64_t nhyp = nwin * iter_num;
+    PCREG_REQUIRE(nhyp < ((int64_t)1 << 26), "pcreg_ransac_batch: more than 2^26 hypotheses in one call");
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    cudaStream_t st = 0;
+    const size_t nel = (size_t)std::max<int64_t>(ntotal, 1);
+    DevBuf<double> d1(nel * 3), d2(nel * 3), dT((size_t)nhyp * 16), dTb((size_t)nwin * 16);
+    DevBuf<int64_t> doff((size_t)nwin + 1), dbest((size_t)nwin), dmax((size_t)nwin), dsucc((size_t)nwin);
+    DevBuf<int32_t> dtri((size_t)nhyp * 3), dcnt((size_t)nhyp), dcntr((size_t)nhyp), dstat((size_t)nwin);
+    DevBuf<unsigned long long> dseed(triplets ? 0 : (size_t)nwin);
+    DevBuf<uint8_t> dflags(nel);
+    for (int a = 0; a < 3; ++a) {
+        PCREG_CUDA(cudaMemcpyAsync(d1.p + a * nel, p1 + a * ld, (size_t)ntotal * 8, cudaMemcpyHostToDevice, st));
+        PCREG_CUDA(cudaMemcpyAsync(d2.p + a * nel, p2 + a * ld, (size_t)ntotal * 8, cudaMemcpyHostToDevice, st));
+    }
+    PCREG_CUDA(cudaMemcpyAsync(doff.p, offsets, ((size_t)nwin + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (triplets) {
+        PCREG_CUDA(cudaMemcpyAsync(dtri.p, triplets, dtri.bytes(), cudaMemcpyHostToDevice, st));
+    } else {
+        PCREG_CUDA(cudaMemcpyAsync(dseed.p, seeds, (size_t)nwin * 8, cudaMemcpyHostToDevice, st));
+        k_gen_triplets_batch<<<(unsigned)((nhyp + 255) / 256), 256, 0, st>>>(dseed.p, doff.p, nwin, iter_num, dtri.p);
+        PCREG_LAUNCHED();
+    }
+    RansacArgs a{};
+    a.p1 = d1.p; a.p2 = d2.p; a.P = 0; a.ld = (int64_t)nel; a.triplets = dtri.p; a.nhyp = nhyp;
+    a.thDist = opts->thDist; a.thInlr = 0.0; a.refine = opts->refine; a.reflection_fix = opts->reflection_fix;
+    a.cnt = dcnt.p; a.cnt_ref = dcntr.p; a.T_rm = dT.p;
+    a.win_off = doff.p; a.hyp_per_win = iter_num; a.ratio = opts->thInlrRatio;
+    k_ransac_score<<<(unsigned)((nhyp * 32 + 255) / 256), 256, 0, st>>>(a);
+    PCREG_LAUNCHED();
+    k_ransac_pick<<<(unsigned)nwin, 256, 0, st>>>(opts->refine ? dcntr.p : dcnt.p, dT.p, doff.p, iter_num, opts->thInlrRatio, dTb.p,
+                                                  dbest.p, dmax.p, dsucc.p, dstat.p);
+    PCREG_LAUNCHED();
+    if (ntotal > 0) {
+        k_inlier_flags_batch<<<(unsigned)((ntotal + 255) / 256), 256, 0, st>>>(d1.p, d2.p, ntotal, (int64_t)nel, doff.p, nwin, dT.p,
+                                                                                dbest.p, iter_num, opts->thDist, dflags.p);
+        PCREG_LAUNCHED();
+    }
+    std::vector<uint8_t> hf((size_t)ntotal);
+    PCREG_CUDA(cudaMemcpyAsync(T16, dTb.p, dTb.bytes(), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaMemcpyAsync(best_hyp, dbest.p, dbest.bytes(), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaMemcpyAsync(max_inl, dmax.p, dmax.bytes(), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaMemcpyAsync(n_succ, dsucc.p, dsucc.bytes(), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaMemcpyAsync(status, dstat.p, dstat.bytes(), cudaMemcpyDeviceToHost, st));
+    if (ntotal > 0) PCREG_CUDA(cudaMemcpyAsync(hf.data(), dflags.p, (size_t)ntotal, cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));
+    for (int64_t w = 0; w < nwin; ++w) {                   // inlierIdx = find(dist < thDist) per window, relative, ascending
+        int64_t ni = 0;
+        if (status[w] == 0)
+            for (int64_t i = offsets[w]; i < offsets[w + 1]; ++i)
+                if (hf[(size_t)i]) inl_idx[offsets[w] + ni++] = (int32_t)(i - offsets[w]);
+        n_inl[w] = ni;
+    }
+    return PCREG_OK;
     PCREG_API_END
 }
 

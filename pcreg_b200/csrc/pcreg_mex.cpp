@@ -20,6 +20,9 @@
 //                                                      -> T, inlierIdx, numSuccess, maxInliers, pct  (ransac.m)
 //   'ransac_seeded', pts1, pts2, coef(struct incl. iterNum), seed
 //                                                      -> same five outputs, samples drawn on the device (pcreg_ransac_run)
+//   'ransac_batch', pts1(Nx3), pts2(Nx3), offsets((W+1)x1, 0-based row offsets of the windows), coef(struct incl. iterNum), seeds(Wx1)
+//                                                      -> T (16xW, NaN where ransac.m returns []), inlierMask (Nx1), numSuccess (Wx1),
+//                                                         maxInliers (Wx1), pct (Wx1)   (one ransac.m call per window, pcreg_ransac_batch)
 //   'local_points', handle, c(Kx3 double), R, min_points, max_points
 //                                                      -> pts_sphere (concatenated, relative to their centre), dists,
 //                                                         counts (Kx1; 0 where the reference returns [])   (getLocalPoints.m)
@@ -264,6 +267,48 @@ bool cmd_ransac(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], bool
     return true;
 }
 
+bool cmd_ransac_batch(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 6 || !mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || !mxIsDouble(prhs[3]) || !mxIsStruct(prhs[4]) || !mxIsDouble(prhs[5]) ||
+        mxGetN(prhs[1]) != 3 || mxGetN(prhs[2]) != 3 || mxGetM(prhs[1]) != mxGetM(prhs[2]) || mxGetNumberOfElements(prhs[3]) < 2 ||
+        mxGetNumberOfElements(prhs[5]) + 1 != mxGetNumberOfElements(prhs[3])) {
+        g_fail = "ransac_batch: need (pts1 Nx3, pts2 Nx3, offsets (W+1), coef, seeds W)";
+        return false;
+    }
+    const int64_t N = (int64_t)mxGetM(prhs[1]);
+    const int64_t W = (int64_t)mxGetNumberOfElements(prhs[5]);
+    const int64_t H = (int64_t)field_or(prhs[4], "iterNum", 1000.0);
+    pcreg_ransac_opts o;
+    o.thDist = field_or(prhs[4], "thDist", 0.5);
+    o.thInlrRatio = field_or(prhs[4], "thInlrRatio", 0.1);
+    o.refine = field_or(prhs[4], "REFINE", 1.0) != 0;
+    o.reflection_fix = 0;
+    std::vector<int64_t> off((size_t)W + 1), n_inl((size_t)W), n_succ((size_t)W), max_inl((size_t)W), best((size_t)W);
+    std::vector<uint64_t> seeds((size_t)W);
+    std::vector<int32_t> inl((size_t)(N > 0 ? N : 1)), status((size_t)W);
+    for (int64_t w = 0; w <= W; ++w) off[(size_t)w] = (int64_t)mxGetPr(prhs[3])[w];
+    for (int64_t w = 0; w < W; ++w) seeds[(size_t)w] = (uint64_t)mxGetPr(prhs[5])[w];
+    if (off[0] != 0 || off[(size_t)W] != N) { g_fail = "ransac_batch: offsets must run from 0 to size(pts1,1)"; return false; }
+    mxArray* T = mxCreateDoubleMatrix(16, (mwSize)W, mxREAL);
+    const int rc = pcreg_ransac_batch(mxGetPr(prhs[1]), mxGetPr(prhs[2]), N > 0 ? N : 1, off.data(), W, H, nullptr, seeds.data(), &o,
+                                      mxGetPr(T), inl.data(), n_inl.data(), n_succ.data(), max_inl.data(), best.data(), status.data());
+    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); mxDestroyArray(T); return false; }
+    plhs[0] = T;
+    if (nlhs > 1) {
+        plhs[1] = mxCreateDoubleMatrix((mwSize)N, 1, mxREAL);                  // zero-filled
+        for (int64_t w = 0; w < W; ++w)
+            for (int64_t k = 0; k < n_inl[(size_t)w]; ++k) mxGetPr(plhs[1])[off[(size_t)w] + inl[(size_t)(off[(size_t)w] + k)]] = 1.0;
+    }
+    for (int k = 2; k < nlhs && k < 5; ++k) {
+        plhs[k] = mxCreateDoubleMatrix((mwSize)W, 1, mxREAL);
+        for (int64_t w = 0; w < W; ++w) {
+            const int64_t Pw = off[(size_t)w + 1] - off[(size_t)w];
+            mxGetPr(plhs[k])[w] = k == 2 ? (double)n_succ[(size_t)w] : k == 3 ? (double)max_inl[(size_t)w]
+                                  : (Pw > 0 ? 100.0 * (double)max_inl[(size_t)w] / (double)Pw : 0.0);
+        }
+    }
+    return true;
+}
+
 bool cmd_get_matches(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs < 4 || !mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || mxIsComplex(prhs[1]) || mxIsComplex(prhs[2]) || !mxIsStruct(prhs[3]) ||
         mxGetN(prhs[1]) != mxGetN(prhs[2])) {
@@ -374,6 +419,7 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
         else if (!strcmp(cmd, "estimate_transform")) ok = cmd_estimate_transform(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "ransac")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs, false);
         else if (!strcmp(cmd, "ransac_seeded")) ok = cmd_ransac(nlhs, plhs, nrhs, prhs, true);
+        else if (!strcmp(cmd, "ransac_batch")) ok = cmd_ransac_batch(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "get_matches")) ok = cmd_get_matches(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "icp")) ok = cmd_icp(nlhs, plhs, nrhs, prhs);
         else g_fail = std::string("pcreg_mex: unknown command '") + cmd + "'";

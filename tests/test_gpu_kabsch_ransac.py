@@ -133,3 +133,75 @@ def test_ransac_seeded_device_sampling_matches_oracle(pcreg):
     assert not np.array_equal(pcreg.ransac_seeded(p1, p2, coef, seed=1, return_triplets=True)["triplets"], tri)
     t3 = oracle.ransac_triplets(5, 50, 3)
     assert np.all(np.sort(t3, axis=1) == np.array([0, 1, 2]))
+
+
+def test_ransac_batch_of_windows_equals_per_window_calls_and_oracle(pcreg):
+    """pcreg_ransac_batch: one call for all matching windows (the reference's parfor over windows,
+    slideMatchingWindow_v2.m:178-198).  Ragged windows incl. an empty one, a 2-pair one (reference would throw in
+    randperm(ptNum)(1:3) -> reported as []), a P = 3 one and one where nothing reaches thInlr; every window must equal
+    the oracle ransac on the documented per-window samples AND the single-window GPU call bit for bit."""
+    sizes = [300, 0, 2, 3, 120, 64, 500]
+    seeds = [11, 12, 13, 14, 15, 16, 2 ** 63 + 5]
+    coef = dict(thDist=0.25, thInlrRatio=0.1, REFINE=True, iterNum=700)
+    g = synth.rng(2024)
+    p1s, p2s = [], []
+    for k, P in enumerate(sizes):
+        if P == 64:                                            # pure outliers: no model found
+            p1s.append(g.uniform(0, 100, (P, 3))); p2s.append(g.uniform(0, 100, (P, 3)))
+        elif P >= 3:
+            a, b, _ = synth.make_ransac_problem(P, 0.35, 0.1, 500 + k)
+            p1s.append(a); p2s.append(b)
+        else:
+            p1s.append(g.uniform(0, 10, (P, 3))); p2s.append(g.uniform(0, 10, (P, 3)))
+    got = pcreg.ransac_batch(p1s, p2s, coef, seeds=seeds)
+    assert len(got) == len(sizes)
+    n_ok = 0
+    for w, P in enumerate(sizes):
+        if P < 3:
+            assert got[w]["T"] is None and got[w]["inlierIdx"].size == 0 and got[w]["numSuccess"] == 0
+            continue
+        tri = oracle.ransac_triplets(seeds[w], coef["iterNum"], P)
+        want = oracle.ransac(p1s[w], p2s[w], coef, tri)
+        single = pcreg.ransac_seeded(p1s[w], p2s[w], coef, seed=seeds[w])
+        if want["T"] is None:
+            assert got[w]["T"] is None and single["T"] is None and got[w]["maxInliers"] == 0 and got[w]["pct"] == 0.0
+            continue
+        n_ok += 1
+        for k in ("best", "numSuccess", "maxInliers"):
+            assert got[w][k] == want[k] == single[k], (w, k)
+        assert abs(got[w]["pct"] - want["pct"]) < 1e-12
+        assert np.array_equal(got[w]["inlierIdx"], want["inlierIdx"]) and np.array_equal(got[w]["inlierIdx"], single["inlierIdx"])
+        assert np.array_equal(got[w]["T"], single["T"])        # same kernel, same arithmetic: bit-identical
+        assert np.linalg.norm(got[w]["T"] - want["T"]) < 1e-9
+    assert n_ok >= 3
+    # explicit per-window triplets instead of seeds
+    tl = [oracle.ransac_triplets(seeds[w], 200, max(P, 3)) for w, P in enumerate(sizes)]
+    got2 = pcreg.ransac_batch(p1s, p2s, coef, triplets_list=tl)
+    for w, P in enumerate(sizes):
+        if P < 3:
+            assert got2[w]["T"] is None
+            continue
+        want = oracle.ransac(p1s[w], p2s[w], coef, tl[w])
+        assert (got2[w]["T"] is None) == (want["T"] is None)
+        if want["T"] is not None:
+            assert got2[w]["best"] == want["best"] and np.array_equal(got2[w]["inlierIdx"], want["inlierIdx"])
+
+
+def test_ransac_batch_reference_driver_shape(pcreg):
+    """slideMatchingWindow_v2.m:146-198 shape: 21 windows x 2e4 iterations, thDist 0.2 (squared), gate > 50 matches."""
+    coef = dict(thDist=0.2, thInlrRatio=0.1, REFINE=True, iterNum=20_000)
+    p1s, p2s, Ts = [], [], []
+    for w in range(21):
+        a, b, T_true = synth.make_ransac_problem(60 + 17 * w, 0.3, 0.1, 900 + w)
+        p1s.append(a); p2s.append(b); Ts.append(T_true)
+    got = pcreg.ransac_batch(p1s, p2s, coef)
+    for w in range(21):
+        assert got[w]["T"] is not None
+        d = oracle.calcDists(got[w]["T"], p1s[w], p2s[w])
+        assert np.array_equal(np.nonzero(d < coef["thDist"])[0], got[w]["inlierIdx"])
+        assert got[w]["maxInliers"] >= 0.2 * p1s[w].shape[0]
+    # spot check two windows completely against the oracle
+    for w in (0, 20):
+        want = oracle.ransac(p1s[w], p2s[w], coef, oracle.ransac_triplets(w, 20_000, p1s[w].shape[0]))
+        assert got[w]["best"] == want["best"] and got[w]["numSuccess"] == want["numSuccess"]
+        assert np.array_equal(got[w]["inlierIdx"], want["inlierIdx"])

@@ -27,7 +27,7 @@ def test_gateway_only_calls_declared_abi():
 def test_matlab_shims_cover_the_reference_signatures():
     d = os.path.join(ROOT, "pcreg_b200", "matlab")
     for name in ("AlignPoints", "AlignPoints_KNN", "AlignPoints_knn", "AlignPoints_weighted", "AlignPoints_c",
-                 "AlignPoints_KNN_c", "estimateTransform", "ransac", "getLocalPoints", "getSpacialHistogramDescriptors", "getMatches"):
+                 "AlignPoints_KNN_c", "estimateTransform", "ransac", "getLocalPoints", "getSpacialHistogramDescriptors", "getMatches", "ransac_windows", "pcreg_icp"):
         with open(os.path.join(d, name + ".m")) as f:
             first = f.readline()
         assert first.startswith("function") and name + "(" in first, first
