@@ -170,6 +170,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long* counters, uns
 constexpr int GRID_ROW_SPAN = 12;
 constexpr int GRID_FETCH_BATCH = 8;
 constexpr int GRID_CHUNK = 32;
+constexpr double GRID_WARP_ROWS_DENSITY = 6.0;      // model points per occupied cell from which the warp-per-query row scan is used
 
 // (sqrt(best) + skin)^2, never too small: the points with d2 <= this value enter the candidate list
 __device__ __forceinline__ double list_thr2(double best, double skin) {
@@ -346,6 +347,209 @@ __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant
             }
             if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p, d, lo);
             ++p;
+        }
+    }
+    flush_counters(a.counters, n_pts, n_cells, 0);
+}
+
+// ---- kernel 1b: row scan, one WARP per query (dense models) ------------------------------------------------
+// Same rows, same points, same exact answer as the per-lane state machine above, but the 32 lanes of a warp work on
+// ONE query at a time: the lanes take the (y,z) rows of the ball (bounds + cell_start pair per lane), a warp scan of
+// the run lengths turns them into one flat range of points, and consecutive lanes take consecutive points of that
+// range (the run of a point is found by a 5-step shuffle search in the scanned lengths), so the gathers of a trip
+// are coalesced runs instead of 32 separate sectors.  Pays when a query visits hundreds of points (many points per
+// occupied cell: C5); on sparse models (C3: ~20 points per query) the single dependent load chain per warp loses
+// against the 32 independent chains of the state machine (measured) -- the launcher picks by density.
+// Setup (pose transform, warm-start bound, cell span) stays lane-parallel: a warp draws 32 consecutive queries, every
+// lane prepares one, then they are processed one after the other with their parameters broadcast by shuffles.  The
+// pruning bound is the warm-start distance, re-tightened between rounds of 32 rows.
+// BUILD: a point enters the list when d2 <= (sqrt(warp's best so far) + skin)^2 -- a superset of the final list,
+// exactly like the sequential rule; entries are appended by ballot compaction.
+#ifndef ROWS_U
+#define ROWS_U 2        // rounds of 32 points whose gathers are in flight together
+#endif
+#ifndef ROWS_BPS
+#define ROWS_BPS 8      // blocks per SM: the kernel is latency bound, occupancy beats the few spilled registers (measured on C5:
+#endif                  // row-scan ms of a 21-pass run  U=1/5 blocks 102, 2/5 89, 4/5 83, 2/6 80, 2/7 86, 1/8 80, 2/8 68; per-lane kernel 125)
+template <bool BUILD>
+__global__ void __launch_bounds__(128, ROWS_BPS) k_nn_grid_rows(const __grid_constant__ GridArgs a) {
+    const GridView& G = a.g;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t total = a.in_list ? (int64_t)*a.in_count : a.nq;
+    if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&a.counters[5], (unsigned long long)total);
+        if (a.in_list) atomicAdd(&a.counters[3], (unsigned long long)(a.nq - total));      // the list scan answered the rest
+    }
+    const double inv_cell2 = G.inv_cell * G.inv_cell;
+    const int dx0 = G.dims[0][0], dy0 = G.dims[0][1], dz0 = G.dims[0][2];
+    unsigned long long n_pts = 0, n_cells = 0;
+
+    while (true) {
+        unsigned long long cbase = 0;
+        if (lane == 0) cbase = atomicAdd(a.cursor, 32ull);
+        cbase = __shfl_sync(FULL, cbase, 0);
+        if ((int64_t)cbase >= total) break;
+        // ---- lane-parallel setup of 32 consecutive queries ----
+        const int64_t cand = (int64_t)cbase + lane;
+        Query Q;
+        int64_t gq = -1;
+        bool ready = false, defer = false, bld = false;
+        int x0 = 0, x1 = -1, y0 = 0, y1 = -1, z0 = 0, z1 = -1, ext_slot = -1;
+        float lo = 0.f;
+        Q.qx = Q.qy = Q.qz = 0.0; Q.fx = Q.fy = Q.fz = 0.f; Q.best = INFINITY; Q.bidx = -1; Q.bestc = 0.f;
+        if (cand < total) {
+            gq = a.in_list ? (int64_t)a.in_list[cand] : cand;
+            float gap = 0.f;
+            if (BUILD) {
+                bld = !a.cl.delta || a.cl.delta[(unsigned)gq / (unsigned)a.ns] <= a.cl.build_max_delta;   // a list pays only once the pose has nearly stopped
+                gap = bld ? a.cl.gap_cells : 0.f;
+            }
+            setup_query(a, gq, Q, gap, a.prev[gq]);
+            if (Q.has_span && Q.ihy - Q.ily < a.row_span && Q.ihz - Q.ilz < a.row_span && Q.ihx - Q.ilx < 4 * a.row_span) {
+                x0 = max(Q.ilx, 0); x1 = min(Q.ihx, dx0 - 1);
+                y0 = max(Q.ily, 0); y1 = min(Q.ihy, dy0 - 1);
+                z0 = max(Q.ilz, 0); z1 = min(Q.ihz, dz0 - 1);
+                ready = true;
+                if (BUILD && bld) {
+                    ext_slot = a.cl.ext[gq];
+                    lo = __fsqrt_rd(__double2float_rd(Q.best)) - (float)a.cl.skin;          // every listed point is within [.., lo + 2 skin]
+                }
+            } else {
+                defer = true;
+            }
+        }
+        worklist_append(a, defer, gq, lane);                 // wide balls go to the walk kernel
+        unsigned todo = __ballot_sync(FULL, ready);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            // ---- broadcast query j ----
+            const double qx = __shfl_sync(FULL, Q.qx, j), qy = __shfl_sync(FULL, Q.qy, j), qz = __shfl_sync(FULL, Q.qz, j);
+            const float fx = __shfl_sync(FULL, Q.fx, j), fy = __shfl_sync(FULL, Q.fy, j), fz = __shfl_sync(FULL, Q.fz, j);
+            double best = __shfl_sync(FULL, Q.best, j);
+            int32_t bidx = __shfl_sync(FULL, Q.bidx, j);
+            float bestc = __shfl_sync(FULL, Q.bestc, j);
+            const int ux0 = __shfl_sync(FULL, x0, j), ux1 = __shfl_sync(FULL, x1, j), uy0 = __shfl_sync(FULL, y0, j),
+                      uy1 = __shfl_sync(FULL, y1, j), uz0 = __shfl_sync(FULL, z0, j), uz1 = __shfl_sync(FULL, z1, j);
+            const int64_t ugq = __shfl_sync(FULL, gq, j);
+            const bool ubld = BUILD && (__shfl_sync(FULL, (int)bld, j) != 0);
+            int uext = BUILD ? __shfl_sync(FULL, ext_slot, j) : -1;
+            const float ulo = BUILD ? __shfl_sync(FULL, lo, j) : 0.f;
+            int lc = 0;
+            const int nyr = uy1 - uy0 + 1;
+            const int nrows = (ux0 > ux1 || uy0 > uy1 || uz0 > uz1) ? 0 : nyr * (uz1 - uz0 + 1);   // 0: nothing to scan, the warm start stands
+            for (int rbase = 0; rbase < nrows; rbase += 32) {
+                // ---- the rows of this round: one per lane ----
+                const int r = rbase + lane;
+                int32_t p = 0, len = 0;
+                if (r < nrows) {
+                    const int zz = uz0 + r / nyr, yy = uy0 + r % nyr;
+                    const float tz = axis_lb(fz, (float)zz, 1.f), ty = axis_lb(fy, (float)yy, 1.f);
+                    const float lb = (ty * ty + tz * tz) * (1.f - 6e-7f);
+                    if (lb <= bestc) {
+                        // cells of this row the ball can reach: |x - fx| <= sqrt(bestc - lb) (+ slop)
+                        const float rx = __fsqrt_ru(bestc - lb) * (1.f + 1e-6f) + 2.f * GRID_SLOP_ABS + GRID_SLOP_REL * fabsf(fx);
+                        const int xa = max(ux0, (int)floorf(fx - rx)), xb = min(ux1, (int)floorf(fx + rx));
+                        if (xa <= xb) {
+                            const int64_t c0 = ((int64_t)zz * dy0 + yy) * dx0;
+                            p = G.cell_start[c0 + xa];
+                            len = G.cell_start[c0 + xb + 1] - p;
+                        }
+                    }
+                }
+                if (len > 0) { ++n_cells; n_pts += (unsigned long long)len; }
+                int incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int T = __shfl_sync(FULL, incl, 31);
+                const int excl = incl - len;
+                // ---- the points of those rows: consecutive lanes take consecutive points of the flat range ----
+                for (int tb = 0; tb < T; tb += 32 * ROWS_U) {
+                    // ROWS_U x 32 points per trip: all their gathers are issued before the first one is used
+                    GridPoint gpu[ROWS_U];
+                    int32_t posu[ROWS_U];
+#pragma unroll
+                    for (int u = 0; u < ROWS_U; ++u) {
+                        const int t = tb + 32 * u + lane;
+                        int s = 0;                               // first row whose inclusive count exceeds t
+#pragma unroll
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            const int v = __shfl_sync(FULL, incl, min(s + step - 1, 31));
+                            if (v <= t) s += step;
+                        }
+                        s = min(s, 31);
+                        const int32_t ps = __shfl_sync(FULL, p, s);
+                        const int ex = __shfl_sync(FULL, excl, s);
+                        posu[u] = (t < T) ? ps + (t - ex) : -1;
+                        if (posu[u] >= 0) gpu[u] = G.pts[posu[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < ROWS_U; ++u) {
+                        if (tb + 32 * u >= T) break;             // warp-uniform
+                        const bool act = posu[u] >= 0;
+                        const int32_t pos = posu[u];
+                        double d = INFINITY;
+                        if (act) {
+                            const GridPoint gp = gpu[u];
+                            d = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
+                            if (d < best || (d == best && gp.orig < bidx)) { best = d; bidx = gp.orig; }
+                        }
+                        if (BUILD && ubld) {
+                            // list threshold from the warp's best so far (an upper bound of the final one)
+                            const unsigned mb = __reduce_min_sync(FULL, __float_as_uint(__double2float_ru(best)));
+                            const double thr2 = list_thr2((double)__uint_as_float(mb), a.cl.skin);
+                            const bool app = act && d <= thr2;
+                            const unsigned am = __ballot_sync(FULL, app);
+                            if (am) {
+                                const int n = __popc(am);
+                                if (lc + n > a.cl.cap && uext == -1) {       // first entry beyond the query's own row: take an extension slot
+                                    unsigned sl = 0;
+                                    if (lane == 0) sl = atomicAdd(a.cl.ext_count, 1u);
+                                    sl = __shfl_sync(FULL, sl, 0);
+                                    uext = sl < (unsigned)a.cl.ext_slots ? (int)sl : -2;                 // -2: pool exhausted
+                                }
+                                if (app) {
+                                    const float sd = __fsqrt_rd(__double2float_rd(d));
+                                    const int level = min(max((int)floorf((sd - ulo) * a.cl.inv_level) - 1, 0), 255);
+                                    const int32_t entry = (int32_t)(((unsigned)pos << 8) | (unsigned)level);
+                                    const int at = lc + __popc(am & lt_mask);
+                                    if (at < a.cl.cap) {
+                                        a.cl.list[ugq * a.cl.cap + at] = entry;
+                                    } else {
+                                        const int k = at - a.cl.cap;
+                                        if (uext >= 0 && k < a.cl.ext_cap) a.cl.ext_list[(int64_t)uext * a.cl.ext_cap + k] = entry;
+                                    }
+                                }
+                                lc += n;
+                            }
+                        }
+                    }
+                }
+                if (rbase + 32 < nrows) {                        // tighten the pruning bound for the next round of rows
+                    const float mb = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(__double2float_ru(best))));
+                    bestc = ubld ? best_ub_cells_gap((double)mb, G.inv_cell, a.cl.gap_cells) : best_ub_cells((double)mb, inv_cell2);
+                }
+            }
+            // ---- the warp's winner on (d2, original index) ----
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(FULL, best, o);
+                const int32_t oi = __shfl_xor_sync(FULL, bidx, o);
+                if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+            }
+            if (lane == j) {
+                a.idx[gq] = bidx;
+                if (a.d2) a.d2[gq] = best;
+                if (BUILD) {
+                    Q.best = best; Q.bidx = bidx;
+                    list_commit(a.cl, G, gq, Q, bld, lc, uext, lo);
+                }
+            }
         }
     }
     flush_counters(a.counters, n_pts, n_cells, 0);
@@ -628,8 +832,18 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
         PCREG_CUDA(cudaMemsetAsync(sc.cursor.p, 0, sizeof(unsigned long long), st));
         a.cursor = sc.cursor.p;
         mark(1);
-        if (cl) k_nn_grid_direct<true><<<direct_blocks, 128, 0, st>>>(a);
-        else    k_nn_grid_direct<false><<<direct_blocks, 128, 0, st>>>(a);
+        // dense models (many points per occupied cell, hundreds of points per query): one warp per query with coalesced
+        // runs; sparse models: the per-lane state machine.  PCREG_ROWSCAN=lane|warp forces one of them.
+        const char* rows_e = getenv("PCREG_ROWSCAN");            // read per launch: the tests flip it inside one process
+        const int rows_env = !rows_e ? 0 : (rows_e[0] == 'w' ? 2 : (rows_e[0] == 'l' ? 1 : 0));
+        const bool warp_rows = rows_env ? rows_env == 2 : (double)m->n >= GRID_WARP_ROWS_DENSITY * (double)std::max<int64_t>(m->g_occupied, 1);
+        if (warp_rows) {
+            if (cl) k_nn_grid_rows<true><<<direct_blocks, 128, 0, st>>>(a);
+            else    k_nn_grid_rows<false><<<direct_blocks, 128, 0, st>>>(a);
+        } else {
+            if (cl) k_nn_grid_direct<true><<<direct_blocks, 128, 0, st>>>(a);
+            else    k_nn_grid_direct<false><<<direct_blocks, 128, 0, st>>>(a);
+        }
         PCREG_LAUNCHED();
         a.in_list = nullptr; a.in_count = nullptr;
         mark(2);

@@ -243,3 +243,31 @@ def test_icp_two_lanes_identical(pcreg, monkeypatch, nn):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c2[k]), k
     assert a["best"] == b["best"] == c2["best"]
     m.destroy()
+
+
+@pytest.mark.parametrize("mode", ["knn", "weighted", "reject"])
+@pytest.mark.parametrize("cpp", [0.0, 0.08])
+def test_icp_warp_row_scan_identical(pcreg, monkeypatch, mode, cpp):
+    """nn_grid.cu has two row-scan kernels: the per-lane state machine (sparse models) and the warp-per-query scan with
+    coalesced runs (dense models, picked by points per occupied cell).  Both, and the brute-force path, must return the
+    same bits -- on the default grid and on a deliberately coarse one (cells_per_point 0.08: ~15-40 points per occupied cell,
+    so the dense path is also what the launcher picks by itself, and the candidate lists overflow into extension slots)."""
+    model = synth.make_model(80_000, 191)
+    src, T_gt, c = synth.make_source(model, 1500, 0.3, 192)
+    T0 = synth.pose_grid(T_gt, c, 3, (2, 2, 2), 8.0, 1.5, 19)[:21]
+    m = pcreg.Model(model, grid=True, cells_per_point=cpp)
+    kw = dict(knn=dict(mode=pcreg.ICP_KNN), weighted=dict(mode=pcreg.ICP_WEIGHTED, R_w=3.5),
+              reject=dict(mode=pcreg.ICP_PLAIN, thDist2=4.0))[mode]
+    ref = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True, **kw)
+    out = {}
+    for rs in ("lane", "warp", None):
+        if rs is None:
+            monkeypatch.delenv("PCREG_ROWSCAN", raising=False)
+        else:
+            monkeypatch.setenv("PCREG_ROWSCAN", rs)
+        out[rs] = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_GRID, return_idx=True, return_hist=True, **kw)
+    for rs, r in out.items():
+        for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+            assert np.array_equal(r[k], ref[k], equal_nan=True) if r[k].dtype.kind == "f" else np.array_equal(r[k], ref[k]), (rs, k)
+        assert r["best"] == ref["best"]
+    m.destroy()
