@@ -4,7 +4,7 @@
 // reference's nearest analogue of a spatially pruned search is speedyDescriptors.m:44-60 (boxes with a
 // halo) and getLocalPoints.m:8-15 (cube pre-filter).
 //
-// Up to three kernels per NN pass, one thread per query in each:
+// Up to three kernels per NN pass (one thread per query unless noted):
 //   k_nn_list         (ICP passes >= 2) queries that own a CANDIDATE LIST -- every model point within
 //                     R_list = r0 + skin of the position q0 the query had when the list was built -- scan it
 //                     exactly.  A point outside the list is farther than R_list - |q - q0| from the moved
@@ -21,6 +21,8 @@
 //                     is appended to a work list (warp-aggregated atomics).
 //                     BUILD variant: the scan is exhaustive within (best distance + gap) and the points within
 //                     (best distance + skin) become the query's new candidate list.
+//   k_nn_grid_rows    the same row scan for DENSE models (>= 6 points per occupied cell): one warp per query, the
+//                     lanes take consecutive points of the ball's rows (coalesced runs), see the kernel.
 //   k_nn_grid_walk    branch-and-bound walk of the occupancy pyramid with a small explicit stack for the
 //                     work list (far queries, and every query of the first iteration).  Keeping the two
 //                     populations in separate launches keeps the lanes of a warp on similar work.
