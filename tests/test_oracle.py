@@ -223,3 +223,32 @@ def test_getmatches_weighting_and_matchfeatures_semantics():
     # SSD: largest possible score 4
     ps, ms = oracle.match_features_exhaustive(dS, -dS, oracle.matching.SSD, 100.0, 1.0, False)
     assert ps.shape[0] == 2 and np.all(ms <= 4.0 + 1e-12)
+
+
+def test_rows_small_golden_is_current():
+    """tests/golden/rows_small.json (AlignPoints* family, ransac, getLocalPoints, getMatches on small seeded inputs) is what
+    the oracle produces today: regenerating it must not change a number."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    G = _golden("rows_small.json")
+    now = json.loads(json.dumps(mg.rows_small(oracle)))
+
+    def same(a, b, path=""):
+        if isinstance(a, dict):
+            assert isinstance(b, dict) and a.keys() == b.keys(), path
+            for k in a:
+                same(a[k], b[k], path + "/" + k)
+        elif isinstance(a, list):
+            assert isinstance(b, list) and len(a) == len(b), path
+            if a and isinstance(a[0], (int, float)) and not isinstance(a[0], bool):
+                assert np.allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=1e-12, atol=1e-12), path
+            else:
+                for i, (x, y) in enumerate(zip(a, b)):
+                    same(x, y, "%s[%d]" % (path, i))
+        elif isinstance(a, float):
+            assert abs(a - b) <= 1e-12 * max(1.0, abs(a)), path
+        else:
+            assert a == b, path
+    same(G, now)
