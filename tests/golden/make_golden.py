@@ -11,8 +11,8 @@ icp_small.json -- outputs of the ORACLE composition (oracle/icp.py) on a small s
   GPU parity test can run without the oracle present.
 rows_small.json -- inputs AND oracle outputs of the other rows of the path on small seeded problems: the six AlignPoints*
   functions (ten call variants) on one neighbourhood, the whole ransac.m call on the documented seeded samples,
-  getLocalPoints for four centres (one of them empty) and getMatches on count-like descriptors whose every decision
-  has a margin above 1e-6.  tests/test_oracle.py checks that the oracle still reproduces it, tests/test_gpu_golden_rows.py
+  getLocalPoints for four centres (one of them empty), getMatches on count-like descriptors whose every decision
+  has a margin above 1e-6, and getSpacialHistogramDescriptors (16 keypoints, 8 survive the point-count / variance checks).  tests/test_oracle.py checks that the oracle still reproduces it, tests/test_gpu_golden_rows.py
   checks the CUDA path against it.
 """
 import json
@@ -118,7 +118,19 @@ def rows_small(o):
     pairs, metric = o.getMatches(dS, dM, MATCH_PAR, return_metric=True)
     out["matches"] = dict(descSurface=dS.tolist(), descModel=dM.tolist(), par=MATCH_PAR, pairs=np.asarray(pairs).tolist(),
                           metric=np.asarray(metric).tolist())
+    # getSpacialHistogramDescriptors: the model is regenerated from its seed (as icp_small.json does), keypoints stored
+    dmodel = np.asarray(synth.make_model(DESC_MODEL[0], DESC_MODEL[1]), dtype=np.float64)
+    g = synth.rng(82)
+    kp = np.vstack([dmodel[g.integers(0, dmodel.shape[0], 12)] + g.normal(0, 0.3, (12, 3)), g.uniform(dmodel.min(0), dmodel.max(0), (4, 3))])
+    feat, desc = o.getSpacialHistogramDescriptors(dmodel, kp, DESC_OPTS) if o is oracle else (None, None)
+    if feat is not None:
+        out["descriptors"] = dict(model=list(DESC_MODEL), keypoints=kp.tolist(), opts=dict(DESC_OPTS, thVar=list(DESC_OPTS["thVar"])),
+                                  feat=np.asarray(feat).tolist(), desc=np.asarray(desc).astype(int).tolist())
     return out
+
+
+DESC_MODEL = (40_000, 81)            # synth.make_model(n, seed)
+DESC_OPTS = dict(min_pts=40, max_pts=2500, R=3.5, thVar=(1.2, 1.5), k=0.85, ALIGN_POINTS=True)
 
 
 def write_rows_small():
@@ -134,6 +146,7 @@ def write_rows_small():
     assert len(m["pairs"]) >= 5
     assert out["ransac"]["maxInliers"] >= 20 and out["align"]["cases"]["AlignPoints_c"]["coeff"] is not None
     assert sum(r["pts"] is None for r in out["local_points"]["results"]) == 1
+    assert 4 <= len(out["descriptors"]["feat"]) < 16
     with open(os.path.join(HERE, "rows_small.json"), "w") as f:
         json.dump(out, f)
 

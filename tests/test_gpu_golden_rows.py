@@ -66,3 +66,17 @@ def test_get_matches_against_committed_fixture(pcreg):
     pairs, metric = pcreg.getMatches(np.asarray(M["descSurface"]), np.asarray(M["descModel"]), M["par"], return_metric=True)
     assert np.asarray(pairs).tolist() == M["pairs"]                     # every decision of the fixture has a margin > 1e-6
     assert np.allclose(metric, np.asarray(M["metric"]), rtol=1e-12, atol=0)
+
+
+def test_descriptors_against_committed_fixture(pcreg):
+    """getSpacialHistogramDescriptors.m: same surviving keypoints, same 980 integer bin counts."""
+    from pcreg_b200 import synth
+    G, _ = _load()
+    D = G["descriptors"]
+    model = np.asarray(synth.make_model(D["model"][0], D["model"][1]), dtype=np.float64)
+    opts = dict(D["opts"], thVar=tuple(D["opts"]["thVar"]))
+    m = pcreg.Model(model)
+    feat, desc = pcreg.getSpacialHistogramDescriptors(m, np.asarray(D["keypoints"]), opts)
+    m.destroy()
+    assert np.array_equal(feat, np.asarray(D["feat"]))
+    assert np.array_equal(np.asarray(desc).astype(np.int64), np.asarray(D["desc"], dtype=np.int64))
