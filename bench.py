@@ -9,7 +9,10 @@ poses per GPU, 5k-point source vs 1M-point model, KNN-trimmed ICP, 30 iterations
 cannot shard; it is measured beside it at N=1 and reported under "c2" (with the brute-force kernel's
 FP32-FMA roofline).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|small]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c2g|c5|small]
+
+--workload c5 = one GPU's share of configs[4] (2048 poses x 65 536 source points vs a 16M-point model that is not
+L2-resident; ~8 s per step, so run it with --steps 2 --no-c2 --no-match --no-cpu).
 
 --impl reference times the CPU oracle restatement (the reference is MATLAB; MATLAB/Octave are probed
 and reported, neither exists in this image) on a bounded sample of the same workload.
