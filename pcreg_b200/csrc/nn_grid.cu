@@ -23,6 +23,8 @@
 //                     (best distance + skin) become the query's new candidate list.
 //   k_nn_grid_rows    the same row scan for DENSE models (>= 6 points per occupied cell): one warp per query, the
 //                     lanes take consecutive points of the ball's rows (coalesced runs), see the kernel.
+//   k_nn_grid_walk_warp  the walk of DENSE models from the third pass on: one warp per query, breadth-first frontier in shared
+//                     memory, leaves scanned like the rows of k_nn_grid_rows; hands overflowing queries to k_nn_grid_walk.
 //   k_nn_grid_walk    branch-and-bound walk of the occupancy pyramid with a small explicit stack for the
 //                     work list (far queries, and every query of the first iteration).  Keeping the two
 //                     populations in separate launches keeps the lanes of a warp on similar work.
@@ -54,6 +56,9 @@ struct GridArgs {
     int32_t* worklist;              // [nq] query ids handed to the next kernel (list -> direct -> walk)
     unsigned int* work_count;       // number of entries in worklist
     unsigned long long* cursor;     // direct kernel: next unassigned position of its input (zeroed before the launch)
+    int32_t* overflow;              // warp walk: queries it hands on to the per-lane walk (frontier too large, no bound)
+    unsigned int* overflow_count;
+    int ww_cap;                     // warp walk: frontier entries it may use (<= WW_CAP; the tests force overflows with a small one)
     int fetch_batch, chunk;         // (tuning)
     int chain;                      // first-pass walk: consecutive queries per thread
     int row_span;                   // direct kernel: widest (y,z) cell span it row-scans itself
@@ -784,6 +789,232 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
     flush_counters(a.counters, n_pts, n_cells, n_nodes, 8, 9);
 }
 
+// ---- kernel 2b: pyramid walk, one WARP per query (dense models, warm-started work list) ----------------------
+// The per-lane walk above scans a dense model's leaves (13 points per occupied cell on C5) one point per lane and
+// trip, at 8-9 active lanes.  Here the 32 lanes descend the pyramid together, level by level: the frontier of nodes whose
+// box can still reach the ball lives in shared memory, one lane takes one (node, child) pair -- occupancy bit, box
+// bound, ballot-compacted append to the next frontier -- and the level-0 frontier (leaf cells) is then handled like the
+// rows of k_nn_grid_rows: a warp scan of the run lengths, consecutive lanes on consecutive points, two gather rounds in
+// flight, the bound re-tightened between rounds of 32 leaves, ballot-compacted list entries (BUILD).  The bound is the
+// warm start, so the breadth-first order costs no pruning power worth mentioning; a query whose frontier outgrows the
+// buffer (or that has no bound) is handed to the per-lane walk through a second work list.  Exactness: identical
+// pruning tests (box_lb vs the upper bound of the best distance, ties never pruned), every visited point in FP64,
+// winner on (d2, original index).
+constexpr int WW_CAP = 512;             // frontier entries per warp
+constexpr int WW_WARPS = 4;
+template <bool BUILD>
+__global__ void __launch_bounds__(32 * WW_WARPS, 6) k_nn_grid_walk_warp(const __grid_constant__ GridArgs a) {
+    __shared__ unsigned s_node[WW_WARPS][2][WW_CAP];     // z << 20 | y << 10 | x
+    __shared__ float s_lb[WW_WARPS][2][WW_CAP];
+    const GridView& G = a.g;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t count = (int64_t)*a.work_count;
+    const double inv_cell2 = G.inv_cell * G.inv_cell;
+    const int dx0 = G.dims[0][0], dy0 = G.dims[0][1];
+    unsigned long long n_pts = 0, n_cells = 0, n_nodes = 0, n_done = 0;
+
+    while (true) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(a.cursor, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if ((int64_t)w >= count) break;
+        // ---- setup, identical on every lane ----
+        const int64_t gq = (int64_t)a.worklist[w];
+        const int32_t warm = a.prev ? a.prev[gq] : -1;
+        bool bld = false;
+        float gap = 0.f;
+        if (BUILD) {
+            bld = !a.cl.delta || a.cl.delta[(unsigned)gq / (unsigned)a.ns] <= a.cl.build_max_delta;
+            gap = bld ? a.cl.gap_cells : 0.f;
+        }
+        Query Q;
+        setup_query(a, gq, Q, gap, warm);
+        bool overflow = !Q.has_span;                         // no bound: the per-lane walk descends from the root
+        const float fx = Q.fx, fy = Q.fy, fz = Q.fz;
+        const double qx = Q.qx, qy = Q.qy, qz = Q.qz;
+        double best = Q.best;
+        int32_t bidx = Q.bidx;
+        float bestc = Q.bestc;
+        int cur = 0, n = 0, level = 0;
+        if (!overflow) {
+            // lowest level whose <= 2 x 2 x 2 nodes cover the ball's bounding cube (else the root)
+            const int top = G.nlevels - 1;
+            int l = 0;
+            while (l < top && (((Q.ihx >> l) - (Q.ilx >> l)) > 1 || ((Q.ihy >> l) - (Q.ily >> l)) > 1 || ((Q.ihz >> l) - (Q.ilz >> l)) > 1)) ++l;
+            level = l;
+            bool ok = false;
+            unsigned nd = 0;
+            float lb = 0.f;
+            if (l == top) {                                      // the root (1 x 1 x 1) wherever the ball lies
+                if (lane == 0) { lb = box_lb(fx, fy, fz, 0, 0, 0, (float)(1 << l)); ok = lb <= bestc; nd = 0u; }
+            } else if (lane < 8) {
+                const int x = (Q.ilx >> l) + (lane & 1), y = (Q.ily >> l) + ((lane >> 1) & 1), z = (Q.ilz >> l) + (lane >> 2);
+                const int dxl = G.dims[l][0], dyl = G.dims[l][1], dzl = G.dims[l][2];
+                if (x <= (Q.ihx >> l) && y <= (Q.ihy >> l) && z <= (Q.ihz >> l) && x >= 0 && y >= 0 && z >= 0 && x < dxl && y < dyl && z < dzl &&
+                    (l == 0 || G.mask[l][((int64_t)z * dyl + y) * dxl + x] != 0)) {
+                    lb = box_lb(fx, fy, fz, x, y, z, (float)(1 << l));
+                    ok = lb <= bestc;
+                    nd = (unsigned)x | ((unsigned)y << 10) | ((unsigned)z << 20);
+                }
+            }
+            const unsigned bm = __ballot_sync(FULL, ok);
+            if (ok) { const int at = __popc(bm & lt_mask); s_node[warp][0][at] = nd; s_lb[warp][0][at] = lb; }
+            n = __popc(bm);
+            __syncwarp();
+        }
+        // ---- descend: frontier at `level` -> frontier at level - 1 ----
+        while (!overflow && level >= 1) {
+            const int dxl = G.dims[level][0], dyl = G.dims[level][1];
+            const float edge = (float)(1 << (level - 1));       // child edge in cells
+            const uint8_t* __restrict__ mk = G.mask[level];
+            int nn = 0;
+            for (int base = 0; base < 8 * n; base += 32) {
+                const int it = base + lane;
+                bool ok = false;
+                unsigned child = 0;
+                float lb = 0.f;
+                if (it < 8 * n) {
+                    const unsigned nd = s_node[warp][cur][it >> 3];
+                    const int k = it & 7;
+                    const int ix = (int)(nd & 1023u), iy = (int)((nd >> 10) & 1023u), iz = (int)(nd >> 20);
+                    const unsigned m = mk[((int64_t)iz * dyl + iy) * dxl + ix];
+                    if ((m >> k) & 1u) {
+                        const int cx = 2 * ix + (k & 1), cy = 2 * iy + ((k >> 1) & 1), cz = 2 * iz + (k >> 2);
+                        lb = box_lb(fx, fy, fz, cx, cy, cz, edge);
+                        ok = lb <= bestc;
+                        child = (unsigned)cx | ((unsigned)cy << 10) | ((unsigned)cz << 20);
+                    }
+                }
+                const unsigned bm = __ballot_sync(FULL, ok);
+                const int at = nn + __popc(bm & lt_mask);
+                if (ok && at < a.ww_cap) { s_node[warp][cur ^ 1][at] = child; s_lb[warp][cur ^ 1][at] = lb; }
+                nn += __popc(bm);
+            }
+            if (lane == 0) n_nodes += (unsigned long long)n;
+            __syncwarp();
+            if (nn > a.ww_cap) { overflow = true; break; }
+            cur ^= 1; n = nn; --level;
+        }
+        if (overflow) {                                          // the per-lane walk takes it from here
+            if (lane == 0) a.overflow[atomicAdd(a.overflow_count, 1u)] = (int32_t)gq;
+            continue;
+        }
+        // ---- leaves: the frontier is a set of level-0 cells ----
+        int lc = 0, uext = -1;
+        float lo = 0.f;
+        if (BUILD && bld) {
+            uext = a.cl.ext[gq];
+            lo = __fsqrt_rd(__double2float_rd(Q.best)) - (float)a.cl.skin;      // every listed point is within [.., lo + 2 skin]
+        }
+        for (int rbase = 0; rbase < n; rbase += 32) {
+            const int r = rbase + lane;
+            int32_t p = 0, len = 0;
+            if (r < n && s_lb[warp][cur][r] <= bestc) {
+                const unsigned nd = s_node[warp][cur][r];
+                const int64_t c = ((int64_t)(nd >> 20) * dy0 + (int64_t)((nd >> 10) & 1023u)) * dx0 + (int64_t)(nd & 1023u);
+                p = G.cell_start[c];
+                len = G.cell_start[c + 1] - p;
+                ++n_cells;
+                n_pts += (unsigned long long)len;
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int T = __shfl_sync(FULL, incl, 31);
+            const int excl = incl - len;
+            // (same point loop as k_nn_grid_rows)
+            for (int tb = 0; tb < T; tb += 32 * ROWS_U) {
+                GridPoint gpu[ROWS_U];
+                int32_t posu[ROWS_U];
+#pragma unroll
+                for (int u = 0; u < ROWS_U; ++u) {
+                    const int t = tb + 32 * u + lane;
+                    int s = 0;                               // first leaf whose inclusive count exceeds t
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, min(s + step - 1, 31));
+                        if (v <= t) s += step;
+                    }
+                    s = min(s, 31);
+                    const int32_t ps = __shfl_sync(FULL, p, s);
+                    const int ex = __shfl_sync(FULL, excl, s);
+                    posu[u] = (t < T) ? ps + (t - ex) : -1;
+                    if (posu[u] >= 0) gpu[u] = G.pts[posu[u]];
+                }
+#pragma unroll
+                for (int u = 0; u < ROWS_U; ++u) {
+                    if (tb + 32 * u >= T) break;             // warp-uniform
+                    const bool act = posu[u] >= 0;
+                    const int32_t pos = posu[u];
+                    double d = INFINITY;
+                    if (act) {
+                        const GridPoint gp = gpu[u];
+                        d = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
+                        if (d < best || (d == best && gp.orig < bidx)) { best = d; bidx = gp.orig; }
+                    }
+                    if (BUILD && bld) {
+                        const unsigned mb = __reduce_min_sync(FULL, __float_as_uint(__double2float_ru(best)));
+                        const double thr2 = list_thr2((double)__uint_as_float(mb), a.cl.skin);
+                        const bool app = act && d <= thr2;
+                        const unsigned am = __ballot_sync(FULL, app);
+                        if (am) {
+                            const int na = __popc(am);
+                            if (lc + na > a.cl.cap && uext == -1) {
+                                unsigned sl = 0;
+                                if (lane == 0) sl = atomicAdd(a.cl.ext_count, 1u);
+                                sl = __shfl_sync(FULL, sl, 0);
+                                uext = sl < (unsigned)a.cl.ext_slots ? (int)sl : -2;
+                            }
+                            if (app) {
+                                const float sd = __fsqrt_rd(__double2float_rd(d));
+                                const int lvl = min(max((int)floorf((sd - lo) * a.cl.inv_level) - 1, 0), 255);
+                                const int32_t entry = (int32_t)(((unsigned)pos << 8) | (unsigned)lvl);
+                                const int at = lc + __popc(am & lt_mask);
+                                if (at < a.cl.cap) {
+                                    a.cl.list[gq * a.cl.cap + at] = entry;
+                                } else {
+                                    const int k = at - a.cl.cap;
+                                    if (uext >= 0 && k < a.cl.ext_cap) a.cl.ext_list[(int64_t)uext * a.cl.ext_cap + k] = entry;
+                                }
+                            }
+                            lc += na;
+                        }
+                    }
+                }
+            }
+            if (rbase + 32 < n) {                            // tighten the bound for the next round of leaves
+                const float mb = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(__double2float_ru(best))));
+                bestc = (BUILD && bld) ? best_ub_cells_gap((double)mb, G.inv_cell, a.cl.gap_cells) : best_ub_cells((double)mb, inv_cell2);
+            }
+        }
+        if (lane == 0) n_nodes += (unsigned long long)n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(FULL, best, o);
+            const int32_t oi = __shfl_xor_sync(FULL, bidx, o);
+            if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if (lane == 0) {
+            a.idx[gq] = bidx;
+            if (a.d2) a.d2[gq] = best;
+            Q.best = best; Q.bidx = bidx;
+            if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, uext, lo);
+            else if (a.cl.cnt) a.cl.cnt[gq] = make_int2(-1, 0);
+            ++n_done;
+        }
+        __syncwarp();
+    }
+    if (a.counters) {
+        flush_counters(a.counters, n_pts, n_cells, n_nodes, 8, 9);
+        if (lane == 0 && n_done) atomicAdd(&a.counters[4], n_done);
+    }
+}
+
 void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy, const double* d_sz, int64_t ns,
                     const double* d_T, int64_t nhyp, const int32_t* d_prev, int32_t* d_idx, double* d_d2,
                     unsigned long long* d_counters, GridScratch& sc, const CandView* cl, bool scan_lists, const double* d_skip_thr,
@@ -849,6 +1080,26 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
         PCREG_LAUNCHED();
         a.in_list = nullptr; a.in_count = nullptr;
         mark(2);
+        // dense models: warp-per-query walk first, the per-lane walk then takes what that one hands on.  PCREG_WALK=lane|warp forces.
+        const char* walk_e = getenv("PCREG_WALK");
+        const int walk_env = !walk_e ? 0 : (walk_e[0] == 'w' ? 2 : (walk_e[0] == 'l' ? 1 : 0));
+        // (from the third NN pass on -- scan_lists is "pass >= 2": right after the first pose update the warm-start bound is loose and the
+        // breadth-first frontier visits 1.6x the points of the nearest-first per-lane walk; measured on C5: 8.0 vs 4.9 ms in that pass)
+        const bool warp_walk = walk_env ? walk_env == 2
+                                        : (scan_lists && (double)m->n >= GRID_WARP_ROWS_DENSITY * (double)std::max<int64_t>(m->g_occupied, 1));
+        if (warp_walk) {
+            if (sc.worklist0.n < (size_t)a.nq) sc.worklist0.alloc((size_t)a.nq);
+            PCREG_CUDA(cudaMemsetAsync(sc.cursor.p, 0, sizeof(unsigned long long), st));     // the row scan is done with both
+            PCREG_CUDA(cudaMemsetAsync(sc.count.p + 1, 0, sizeof(unsigned int), st));
+            a.overflow = sc.worklist0.p; a.overflow_count = sc.count.p + 1;
+            const char* cap_e = getenv("PCREG_WW_CAP");
+            a.ww_cap = cap_e ? std::min(std::max(atoi(cap_e), 8), WW_CAP) : WW_CAP;          // >= 8: the start frontier always fits
+            const int ww_blocks = (int)std::min<int64_t>((a.nq + WW_WARPS - 1) / WW_WARPS, (int64_t)ctx().sm_count * 12);
+            if (cl) k_nn_grid_walk_warp<true><<<ww_blocks, 32 * WW_WARPS, 0, st>>>(a);
+            else    k_nn_grid_walk_warp<false><<<ww_blocks, 32 * WW_WARPS, 0, st>>>(a);
+            PCREG_LAUNCHED();
+            a.worklist = sc.worklist0.p; a.work_count = sc.count.p + 1;
+        }
         if (cl) k_nn_grid_walk<true><<<walk_blocks, 128, 0, st>>>(a);
         else    k_nn_grid_walk<false><<<walk_blocks, 128, 0, st>>>(a);
         PCREG_LAUNCHED();

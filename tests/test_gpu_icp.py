@@ -248,9 +248,9 @@ def test_icp_two_lanes_identical(pcreg, monkeypatch, nn):
 @pytest.mark.parametrize("mode", ["knn", "weighted", "reject"])
 @pytest.mark.parametrize("cpp", [0.0, 0.08])
 def test_icp_warp_row_scan_identical(pcreg, monkeypatch, mode, cpp):
-    """nn_grid.cu has two row-scan kernels: the per-lane state machine (sparse models) and the warp-per-query scan with
-    coalesced runs (dense models, picked by points per occupied cell).  Both, and the brute-force path, must return the
-    same bits -- on the default grid and on a deliberately coarse one (cells_per_point 0.08: ~15-40 points per occupied cell,
+    """nn_grid.cu has two row-scan kernels and two pyramid-walk kernels: per-lane (sparse models) and warp-per-query with
+    coalesced runs (dense models, picked by points per occupied cell; the warp walk hands queries whose frontier outgrows its
+    buffer to the per-lane walk).  All of them, and the brute-force path, must return the same bits -- on the default grid and on a deliberately coarse one (cells_per_point 0.08: ~15-40 points per occupied cell,
     so the dense path is also what the launcher picks by itself, and the candidate lists overflow into extension slots)."""
     model = synth.make_model(80_000, 191)
     src, T_gt, c = synth.make_source(model, 1500, 0.3, 192)
@@ -260,11 +260,14 @@ def test_icp_warp_row_scan_identical(pcreg, monkeypatch, mode, cpp):
               reject=dict(mode=pcreg.ICP_PLAIN, thDist2=4.0))[mode]
     ref = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True, **kw)
     out = {}
-    for rs in ("lane", "warp", None):
-        if rs is None:
-            monkeypatch.delenv("PCREG_ROWSCAN", raising=False)
-        else:
-            monkeypatch.setenv("PCREG_ROWSCAN", rs)
+    for rs in ("lane", "warp", "warp-overflow", None):
+        for var in ("PCREG_ROWSCAN", "PCREG_WALK", "PCREG_WW_CAP"):
+            monkeypatch.delenv(var, raising=False)
+        if rs is not None:                                   # the same choice for the row scan and for the pyramid walk
+            monkeypatch.setenv("PCREG_ROWSCAN", rs.split("-")[0])
+            monkeypatch.setenv("PCREG_WALK", rs.split("-")[0])
+        if rs == "warp-overflow":                            # a frontier of 8 nodes: most walked queries are handed on to the per-lane walk
+            monkeypatch.setenv("PCREG_WW_CAP", "8")
         out[rs] = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_GRID, return_idx=True, return_hist=True, **kw)
     for rs, r in out.items():
         for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
