@@ -91,7 +91,7 @@ bool cmd_nn_search(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     mxArray* d2 = mxCreateDoubleMatrix((mwSize)nq, 1, mxREAL);
     const int kind = (nrhs > 3) ? PCREG_NN_GRID : PCREG_NN_BRUTE;
     const int rc = pcreg_nn_search(m, mxGetData(prhs[2]), mxIsDouble(prhs[2]), nq, nq, kind, idx.data(), mxGetPr(d2));
-    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); mxDestroyArray(d2); return false; }
+    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); mxDestroyArray(d2); mxDestroyArray(plhs[0]); plhs[0] = nullptr; return false; }
     double* o = mxGetPr(plhs[0]);
     for (int64_t i = 0; i < nq; ++i) o[i] = (double)idx[(size_t)i] + 1.0;
     if (nlhs > 1) plhs[1] = d2; else mxDestroyArray(d2);

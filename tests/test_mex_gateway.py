@@ -1,5 +1,7 @@
-"""The MEX gateway cannot run here (no MATLAB / Octave / mex.h in the image); it is at least type-checked
-against a stand-in mex.h, and every ABI symbol it calls must be declared in include/pcreg.h."""
+"""The MEX gateway cannot run under MATLAB here (no MATLAB / Octave / mex.h in the image).  It is type-checked against a
+stand-in mex.h, every ABI symbol it calls must be declared in include/pcreg.h, and its marshaling is EXECUTED against an
+in-memory fake of the mx* runtime with stubs of the C ABI (tests/fake_mex/gateway_harness.cpp): 1-based <-> 0-based
+indices, column-major layouts, struct parsing, [] for degenerate results, error text, no leaked arrays."""
 import os
 import re
 import subprocess
@@ -12,6 +14,16 @@ def test_gateway_typechecks_against_fake_mex():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "fake_mex"), src],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_gateway_marshaling_runs_against_fake_runtime(tmp_path):
+    exe = str(tmp_path / "gateway_harness")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "fake_mex"),
+                        os.path.join(ROOT, "tests", "fake_mex", "gateway_harness.cpp"),
+                        os.path.join(ROOT, "pcreg_b200", "csrc", "pcreg_mex.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK:"), r.stdout + r.stderr
 
 
 def test_gateway_only_calls_declared_abi():
