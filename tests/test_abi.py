@@ -84,3 +84,21 @@ def test_product_package_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     txt = f.read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), fn
+
+
+def test_header_is_plain_c99_and_links_from_c(built, tmp_path):
+    """The drop-in boundary is a C ABI: include/pcreg.h must compile as C99 (no C++-isms, no torch types) and a C program
+    must link against the library and call a non-compute entry point (no GPU needed for that)."""
+    src = tmp_path / "c_user.c"
+    src.write_text('#include <stdio.h>\n#include "pcreg.h"\n'
+                   'int main(void) { pcreg_icp_opts o; pcreg_icp_opts_default(&o);\n'
+                   '  printf("%d %d %.2f\\n", pcreg_abi_version(), o.iters, o.k_frac);\n'
+                   '  return (pcreg_abi_version() > 0 && o.k_frac == 0.85) ? 0 : 1; }\n')
+    import subprocess
+    exe = tmp_path / "c_user"
+    libdir = os.path.dirname(built)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-L", libdir, "-l:" + os.path.basename(built), "-Wl,-rpath," + libdir, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
