@@ -304,6 +304,8 @@ def gpu_workload(P, torch, w, rank, steps, warmup, dist=None, world=1, e2e_steps
     d2h = h_T.numel() * 8 + h_rmse.numel() * 8 + h_nu.numel() * 4 + h_st.numel() * 4 + 8
     ok_e2e = bool(np.allclose(h_rmse.numpy(), out.rmse.cpu().numpy(), rtol=0, atol=0, equal_nan=True))
     grid = m.grid_info() if w["nn"] == "grid" else None
+    if grid is not None:
+        grid["voxel_map"] = m.voxel_info()
     m.destroy()
     q_per_step = H * ns * (w["iters"] + 1)
     return dict(ms_per_step=ms / steps, ms_per_step_e2e=ms_e2e / e2e_steps, q_per_step=q_per_step, H=H, ns=ns, launches=launches,
@@ -315,6 +317,34 @@ def roofline_for(w, r):
     """Roofline of the dominant kernel of the workload, from the profiled step (CUDA events around every launch
     inside the library + exact device-side work counters).  Algorithmic bytes as defined in DESIGN.md section 3."""
     p = r["prof"]
+    if w["nn"] == "grid" and p.get("voxel_map"):
+        # Voronoi voxel map: per query 24-byte source point + 8-byte voxel header + 12-byte result, 16 bytes per list entry
+        # scanned, 32 bytes per point gathered for the FP64 decision; the rest of the queries is walked (counters as below)
+        peak, how = hbm_peak()
+        kern = {
+            "k_nn_vox": dict(ms=p["list_ms"], launches=p["list_launches"],
+                             bytes=8.0 * p["nn_queries"] + 36.0 * p["certified_queries"] + 16.0 * p["list_entries_read"]
+                                   + 32.0 * p["list_points_gathered"]),
+            "k_nn_grid_walk": dict(ms=p["walk_ms"], launches=p["walk_launches"],
+                                   bytes=36.0 * p["walked_queries"] + 8.0 * p["walk_leaves"] + 32.0 * p["walk_points"]
+                                         + 1.0 * max(0.0, p["grid_nodes_popped"] - p["walk_leaves"])),
+            "k_icp_update": dict(ms=p["update_ms"], launches=p["update_launches"], bytes=76.0 * p["correspondences"]),
+        }
+        for k, v in kern.items():
+            v["gbs"] = v["bytes"] / max(v["ms"], 1e-9) / 1e6
+            v["frac"] = v["gbs"] / peak
+            v["traffic"] = ncu_traffic(k)
+        top = max(kern, key=lambda k: kern[k]["ms"])
+        t = kern[top]
+        launches = max(1.0, t["launches"])
+        return dict(bound="hbm", kernel=top, achieved=t["gbs"], peak=peak, unit="GB/s", frac=t["frac"], traffic=t["traffic"],
+                    peak_source=how, bytes_per_launch=t["bytes"] / launches, avg_launch_ms=t["ms"] / launches,
+                    note="algorithmic bytes from exact device-side counters (DESIGN.md 3.2)",
+                    kernels={k: dict(ms=v["ms"], launches=v["launches"], algorithmic_bytes=v["bytes"], gbs=v["gbs"], frac=v["frac"],
+                                     traffic=v["traffic"]) for k, v in kern.items()},
+                    list_answered_fraction=p["certified_queries"] / max(1.0, p["nn_queries"]),
+                    entries_per_query=p["list_entries_read"] / max(1.0, p["certified_queries"]),
+                    fp64_points_per_query=p["list_points_gathered"] / max(1.0, p["certified_queries"]))
     if w["nn"] == "grid":
         peak, how = hbm_peak()
         nq_pass = r["H"] * r["ns"]

@@ -54,6 +54,14 @@ typedef struct {
     double  cells_per_point;   /* automatic sizing target, <= 0 -> 32                                       */
     int64_t max_cells;         /* cap on level-0 cells, <= 0 -> 2^27                                        */
     uint64_t shuffle_seed;     /* seed of the brute-force scan order permutation (any value; 0 is fine)     */
+    /* Voronoi voxel map on top of the grid (build_grid = 1): every voxel of a uniform grid over the padded bounding
+     * box lists the model points that can be the nearest neighbour of a location inside it, so a grid-NN query is one
+     * short contiguous list scan (nn_vox.cu).  Costs HBM (header 8 B per voxel + 16 B per entry).                   */
+    int     voxel_map;         /* 0: automatic (built unless the model is too dense for the budget), 1: always, -1: never */
+    double  voxel_scale;       /* voxel edge in units of the estimated point spacing, <= 0 -> 1.25                   */
+    double  voxel_margin;      /* padding around the bounding box (model units); 0 -> 4 % of the largest extent, < 0 -> none.
+                                  Queries outside the padded box are answered by the pyramid walk.                    */
+    int64_t max_voxels;        /* cap on the number of voxels, <= 0 -> min(2^27, device memory / 1024 B)             */
 } pcreg_model_opts;
 
 /* Upload a model cloud (the dense CT/MRI cloud every driver loads once: completeExperiment.m:15,
@@ -65,6 +73,9 @@ int  pcreg_model_destroy(pcreg_model* m);
 int64_t pcreg_model_size(const pcreg_model* m);
 /* Grid facts for roofline accounting: dims[3], cell size, number of non-empty level-0 cells. */
 int  pcreg_model_grid_info(const pcreg_model* m, int32_t dims[3], double* cell_size, int64_t* occupied);
+/* Voxel-map facts (all zero when the model has none): dims[3], voxel edge, stats = {voxels, voxels with a list, entries,
+ * voxels without a list because it was too long, ... because the pool was full, longest list, build time in us, bytes}. */
+int  pcreg_model_voxel_info(const pcreg_model* m, int32_t dims[3], double* voxel_size, int64_t stats[8]);
 
 /* ---- nearest neighbour (knnsearch(model, q, 'K', 1) semantics: Euclidean, FP64, ties -> smallest
  *      index; the reference's only literal cloud->cloud 1-NN loop is ColorCodeModel.m:15-18) ---- */
@@ -261,7 +272,10 @@ int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
  *   out[15] = model points / out[16] = leaf cells visited by the walk;
  *   out[17..19] = total ms and out[20..22] = launches of the list-scan / row-scan / walk kernels,
  *   out[23] = queries whose search was skipped by lazy trimming (they are included in out[10]);
- *   after pcreg_get_matches: out[24] = total ms of the score kernel, out[25] = (pair, dimension) terms it evaluated.
+ *   after pcreg_get_matches: out[24] = total ms of the score kernel, out[25] = (pair, dimension) terms it evaluated;
+ *   out[26] = 1 when the grid NN ran on the model's Voronoi voxel map: then out[10] = queries answered by the voxel list
+ *   scan, out[13] = list entries read, out[14] = points gathered for the FP64 decision, out[17] / out[20] = ms / launches
+ *   of the list-scan kernel, and out[11], out[15], out[16], out[9], out[19] describe the pyramid walk of the rest.
  * Collected only when enabled: the counters add atomics to the kernels, so timed runs keep it off. */
 int  pcreg_set_profiling(int enabled);
 int  pcreg_last_profile(double out[32]);

@@ -23,7 +23,8 @@ class PcregError(RuntimeError):
 
 class ModelOpts(C.Structure):
     _fields_ = [("build_grid", C.c_int), ("cell_size", C.c_double), ("cells_per_point", C.c_double),
-                ("max_cells", C.c_int64), ("shuffle_seed", C.c_uint64)]
+                ("max_cells", C.c_int64), ("shuffle_seed", C.c_uint64),
+                ("voxel_map", C.c_int), ("voxel_scale", C.c_double), ("voxel_margin", C.c_double), ("max_voxels", C.c_int64)]
 
 
 class AlignOpts(C.Structure):
@@ -61,6 +62,7 @@ SIGNATURES = {
     "pcreg_model_destroy": (C.c_int, [C.c_void_p]),
     "pcreg_model_size": (C.c_int64, [C.c_void_p]),
     "pcreg_model_grid_info": (C.c_int, [C.c_void_p, c_i32p, c_f64p, c_i64p]),
+    "pcreg_model_voxel_info": (C.c_int, [C.c_void_p, c_i32p, c_f64p, c_i64p]),
     "pcreg_nn_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, c_i32p, c_f64p]),
     "pcreg_local_points_count": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, c_i64p, c_i32p]),
     "pcreg_local_points_fill": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.c_double, c_i64p, c_i32p, c_f64p, C.c_int64,

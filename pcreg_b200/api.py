@@ -53,13 +53,16 @@ def _T_from_abi(buf, n=None):
 # model handle
 # ------------------------------------------------------------------------------------------------
 class Model:
-    """GPU-resident model cloud (pcreg_model_create).  ``grid=True`` also builds the uniform grid."""
+    """GPU-resident model cloud (pcreg_model_create).  ``grid=True`` also builds the uniform grid and, unless
+    ``voxel_map=-1`` (or the model is too dense for the memory budget), the Voronoi voxel map on top of it."""
 
     def __init__(self, pts, grid: bool = False, cell_size: float = 0.0, cells_per_point: float = 0.0,
-                 max_cells: int = 0, shuffle_seed: int = 0):
+                 max_cells: int = 0, shuffle_seed: int = 0, voxel_map: int = 0, voxel_scale: float = 0.0,
+                 voxel_margin: float = 0.0, max_voxels: int = 0):
         lib = L.lib()
         a, is_double, n = _cm_points(pts)
-        opts = ModelOpts(int(bool(grid)), float(cell_size), float(cells_per_point), int(max_cells), int(shuffle_seed))
+        opts = ModelOpts(int(bool(grid)), float(cell_size), float(cells_per_point), int(max_cells), int(shuffle_seed),
+                         int(voxel_map), float(voxel_scale), float(voxel_margin), int(max_voxels))
         h = C.c_void_p()
         L.check(lib.pcreg_model_create(a.ctypes.data_as(C.c_void_p), is_double, n, n, C.byref(opts), C.byref(h)),
                 "pcreg_model_create")
@@ -79,6 +82,15 @@ class Model:
         occ = C.c_int64()
         L.check(L.lib().pcreg_model_grid_info(self.handle, dims, C.byref(cell), C.byref(occ)), "pcreg_model_grid_info")
         return dict(dims=tuple(dims), cell_size=cell.value, occupied=occ.value)
+
+    def voxel_info(self):
+        """Voronoi voxel map facts (dims all zero when the model has none)."""
+        dims = (C.c_int32 * 3)()
+        vs = C.c_double()
+        st = (C.c_int64 * 8)()
+        L.check(L.lib().pcreg_model_voxel_info(self.handle, dims, C.byref(vs), st), "pcreg_model_voxel_info")
+        return dict(dims=tuple(dims), voxel_size=vs.value, voxels=st[0], listed=st[1], entries=st[2], too_long=st[3],
+                    no_room=st[4], max_len=st[5], build_ms=st[6] / 1000.0, bytes=st[7])
 
     def nn_search(self, q, nn: int = NN_BRUTE):
         """knnsearch(model, q, 'K', 1): returns (idx int32 [nq] 0-based, d2 float64 [nq] squared distance)."""
@@ -495,7 +507,7 @@ def last_profile() -> dict:
                 list_entries_read=v[13], list_points_gathered=v[14],
                 rowscan_points=v[7], rowscan_rows=v[8], walk_points=v[15], walk_leaves=v[16],
                 list_ms=v[17], rowscan_ms=v[18], walk_ms=v[19], list_launches=v[20], rowscan_launches=v[21], walk_launches=v[22],
-                match_score_ms=v[24], match_terms=v[25])
+                match_score_ms=v[24], match_terms=v[25], voxel_map=v[26])
 
 
 def launch_count() -> int:

@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpcreg_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["model.cu", "nn_brute.cu", "nn_grid.cu", "icp.cu", "kabsch_ransac.cu", "align.cu", "local_points.cu", "descriptor.cu", "match.cu"]
-HEADERS = ["pcreg_internal.h", "pcreg_dev.cuh", "pcreg_math.cuh", "pcreg_select.cuh", os.path.join("..", "..", "include", "pcreg.h")]
+SOURCES = ["model.cu", "nn_brute.cu", "nn_grid.cu", "nn_vox.cu", "icp.cu", "kabsch_ransac.cu", "align.cu", "local_points.cu", "descriptor.cu", "match.cu"]
+HEADERS = ["pcreg_internal.h", "pcreg_dev.cuh", "pcreg_math.cuh", "pcreg_select.cuh", "pcreg_grid.cuh", os.path.join("..", "..", "include", "pcreg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

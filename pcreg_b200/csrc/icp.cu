@@ -195,9 +195,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_cons
         if (a.skip_thr) {
             double thr = INFINITY;
             if (a.update && a.delta) {
-                thr = (trim_tau + 2.0 * (double)moved) * (1.0 + 1e-9);
-                if (reject) thr = fmin(thr, (sqrt(a.thDist2) + (double)moved) * (1.0 + 1e-9));
-                if (a.mode == PCREG_ICP_WEIGHTED) thr = fmin(thr, (a.R_w + (double)moved) * (1.0 + 1e-9));
+                // The skipping kernel replaces the residual by  nl = sd (1 - 1e-12) - moved (1 + 1e-6)  and skips when
+                // sd (1 - 1e-12) > thr: with thr = bound (1 + 1e-9) + moved (1 + 2e-6) the stored stand-in stays STRICTLY above the
+                // bound it must stay above (tau + moved for the trim, sqrt(thDist2) for the rejection, R_w for the weights).
+                const double mv = (double)moved * (1.0 + 2e-6);
+                thr = (trim_tau + (double)moved) * (1.0 + 1e-9) + mv;
+                if (reject) thr = fmin(thr, sqrt(a.thDist2) * (1.0 + 1e-9) + mv);
+                if (a.mode == PCREG_ICP_WEIGHTED) thr = fmin(thr, a.R_w * (1.0 + 1e-9) + mv);
             }
             a.skip_thr[h] = thr;
         }
@@ -388,7 +392,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
 
     // chunk the hypotheses so that the per-correspondence scratch stays bounded
     const size_t total_b = c.total_mem;         // queried once at pcreg_init (cudaMemGetInfo costs up to tens of ms per call)
-    const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + 28 + 4 * 64 + 4 * 448 / 16 : 0));
+    const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + (m->has_vox ? 0 : 28 + 4 * 64 + 4 * 448 / 16) : 0));
     const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)24 << 30, total_b / 6));
     // Two sub-batches ("lanes") on two streams: every kernel of the loop is latency bound with a tail (a few slow
     // queries, a block per hypothesis), so the kernels of one lane fill the gaps of the other.  Profiling runs use one
@@ -415,7 +419,8 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     static const bool lists_on = [] { const char* e = getenv("PCREG_LISTS"); return !(e && e[0] == '0'); }();
     static const double list_skin_cells = [] { const char* e = getenv("PCREG_LIST_SKIN"); return e ? atof(e) : 0.5; }();
     static const int list_cap = [] { const char* e = getenv("PCREG_LIST_CAP"); int v = e ? atoi(e) : 64; return std::max(4, (v + 3) & ~3); }();
-    const bool use_lists = (o.nn == PCREG_NN_GRID) && lists_on && o.iters >= 3 && m->n <= ((int64_t)1 << 24);
+    // (a model with a Voronoi voxel map answers every pass with one list scan per query: no per-query lists, nn_vox.cu)
+    const bool use_lists = (o.nn == PCREG_NN_GRID) && lists_on && o.iters >= 3 && m->n <= ((int64_t)1 << 24) && !m->has_vox;
     const int ext_cap = 448;                                               // wide balls: up to list_cap + 448 candidates
     const int64_t ext_slots = use_lists ? std::max<int64_t>(1024, hc * ns / 16) : 0;
     DevBuf<float> delta(use_lists ? (size_t)nhyp : 0);
@@ -609,6 +614,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         c.profile[3] = (o.nn == PCREG_NN_BRUTE) ? nq * (double)m->n : 0.0;
         c.profile[4] = upd_launches; c.profile[5] = upd_ms; c.profile[6] = nq;
         c.profile[7] = (double)hcnt[0]; c.profile[8] = (double)hcnt[1]; c.profile[9] = (double)hcnt[2];
+        c.profile[26] = (o.nn == PCREG_NN_GRID && m->has_vox) ? 1.0 : 0.0;
     }
 }
 
@@ -720,6 +726,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         c.profile[0] = 1; c.profile[1] = ms; c.profile[2] = (double)nq;
         c.profile[3] = nn_kind == PCREG_NN_BRUTE ? (double)nq * (double)m->n : 0.0;
         c.profile[7] = (double)hcnt[0]; c.profile[8] = (double)hcnt[1]; c.profile[9] = (double)hcnt[2];
+        c.profile[26] = (nn_kind == PCREG_NN_GRID && m->has_vox) ? 1.0 : 0.0;
     }
     return PCREG_OK;
     PCREG_API_END

@@ -383,7 +383,7 @@ using namespace pcreg;
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int pcreg_abi_version(void) { return 1; }
+int pcreg_abi_version(void) { return 2; }
 const char* pcreg_last_error(void) { return g_err[0] ? g_err : g_err_global; }
 int64_t pcreg_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -489,7 +489,10 @@ int pcreg_model_create(const void* xyz, int is_double, int64_t n, int64_t ld, co
     PCREG_CUDA(cudaMemcpyAsync(m->perm.p, perm.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     k_build_m4<<<(unsigned)((m->n_pad + 255) / 256), 256, 0, st>>>(m->md.p, m->perm.p, n, m->n_pad, m->pivot[0], m->pivot[1], m->pivot[2], m->m4.p);
     PCREG_LAUNCHED();
-    if (o.build_grid) grid_build(m.get(), o, st);
+    if (o.build_grid) {
+        grid_build(m.get(), o, st);
+        vox_build(m.get(), o, st);
+    }
     PCREG_CUDA(cudaStreamSynchronize(st));
     *out = m.release();
     return PCREG_OK;

@@ -39,36 +39,15 @@
 
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
+#include "pcreg_grid.cuh"
 
 namespace pcreg {
 
-struct GridArgs {
-    GridView g;
-    const ModelPointD* md;
-    const double* sx; const double* sy; const double* sz; int64_t ns;
-    const double* T; int64_t nq;
-    const int32_t* prev;
-    int32_t* idx; double* d2;
-    CandView cl;                    // candidate lists of the chunk (cl.cnt == nullptr: disabled)
-    const double* skip_thr;         // [nhyp] or null: list kernel skips queries whose previous residual exceeds it (lazy trimming)
-    const int32_t* in_list;         // direct kernel: the queries to process (nullptr: all nq)
-    const unsigned int* in_count;   //                and how many
-    int32_t* worklist;              // [nq] query ids handed to the next kernel (list -> direct -> walk)
-    unsigned int* work_count;       // number of entries in worklist
-    unsigned long long* cursor;     // direct kernel: next unassigned position of its input (zeroed before the launch)
-    int32_t* overflow;              // warp walk: queries it hands on to the per-lane walk (frontier too large, no bound)
-    unsigned int* overflow_count;
-    int ww_cap;                     // warp walk: frontier entries it may use (<= WW_CAP; the tests force overflows with a small one)
-    int fetch_batch, chunk;         // (tuning)
-    int chain;                      // first-pass walk: consecutive queries per thread
-    int row_span;                   // direct kernel: widest (y,z) cell span it row-scans itself
-    unsigned long long* counters;   // profiling only (may be null): [0] points / [1] rows visited by the row scan, [2] pyramid
-                                    // nodes popped, [3] queries answered from their list, [4] queries walked, [5] queries
-                                    // row-scanned, [6] list entries read, [7] list points gathered, [8] points / [9] leaf cells
-                                    // visited by the walk
-};
-
 constexpr int GRID_STACK = 80;
+// depth-first walk: starts from the root (1 entry, GRID_MAX_LEVELS - 1 levels to descend) or from <= 8 nodes below it;
+// every expanded node replaces itself by at most 8 children (net +7 per level)
+static_assert(1 + 7 * (GRID_MAX_LEVELS - 1) <= GRID_STACK && 8 + 7 * (GRID_MAX_LEVELS - 2) <= GRID_STACK,
+              "k_nn_grid_walk: explicit stack too small for GRID_MAX_LEVELS");
 constexpr float GRID_SLOP_ABS = 1.3e-4f;   // cell units: FP32 rounding of the query (<= 1024 cells) + of the difference
 constexpr float GRID_SLOP_REL = 2.5e-7f;
 
@@ -146,23 +125,6 @@ __device__ __forceinline__ void scan_points(const GridView& G, int32_t s0, int32
     if (improved) Q.bestc = best_ub_cells(Q.best, inv_cell2);
 }
 
-__device__ __forceinline__ void flush_counters(unsigned long long* counters, unsigned long long n_pts,
-                                               unsigned long long n_cells, unsigned long long n_nodes, int i_pts = 0, int i_cells = 1,
-                                               int i_nodes = 2) {
-    if (!counters) return;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_pts += __shfl_xor_sync(0xffffffffu, n_pts, o);
-        n_cells += __shfl_xor_sync(0xffffffffu, n_cells, o);
-        n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_pts) atomicAdd(&counters[i_pts], n_pts);
-        if (n_cells) atomicAdd(&counters[i_cells], n_cells);
-        if (n_nodes) atomicAdd(&counters[i_nodes], n_nodes);
-    }
-}
-
 // ---- kernel 1: row scan ----------------------------------------------------------------------------------
 // Cells of one x-row are contiguous in memory, so for a fixed (y,z) the cells the ball can touch are ONE
 // run of points [cell_start[row + xa], cell_start[row + xb + 1]).  A query whose bounding cube spans at
@@ -184,18 +146,6 @@ __device__ __forceinline__ double list_thr2(double best, double skin) {
     const double t = sqrt(best) + skin;
     return t * t * (1.0 + 1e-12);
 }
-// warp-aggregated append of query ids to the next kernel's work list
-__device__ __forceinline__ void worklist_append(const GridArgs& a, bool defer, int64_t gq, int lane) {
-    const unsigned dm = __ballot_sync(0xffffffffu, defer);
-    if (dm) {
-        const int leader = __ffs(dm) - 1;
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(a.work_count, (unsigned)__popc(dm));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (defer) a.worklist[base + __popc(dm & ((1u << lane) - 1u))] = (int32_t)gq;
-    }
-}
-
 // append grid position p to the list under construction: the first cl.cap entries live in the query's own
 // row, longer lists (wide balls) continue in an extension slot taken from a shared pool on first need
 // entry = position << 8 | level, level = where sqrt(d2) falls in [lo, lo + 2 skin] on a 256-step scale, rounded DOWN by
@@ -775,8 +725,10 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
                     m &= ~(1u << t);
                     const int k = t ^ (int)oct;
                     const float lb = ((((k & 1) ? ax1 : ax0) + ((k & 2) ? ay1 : ay0)) + ((k & 4) ? az1 : az0)) * (1.f - 6e-7f);
-                    if (lb <= Q.bestc && sp < GRID_STACK)
+                    if (lb <= Q.bestc) {
+                        if (sp >= GRID_STACK) __trap();            // unreachable (static_assert below): never drop a node silently
                         stack[sp++] = pack_entry(lb, level - 1, 2 * ix + (k & 1), 2 * iy + ((k >> 1) & 1), 2 * iz + (k >> 2));
+                    }
                 }
             }
             a.idx[gq] = Q.bidx;
@@ -1032,7 +984,7 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
     static const int ch_env = [] { const char* e = getenv("PCREG_CHUNK"); return e ? atoi(e) : 0; }();
     static const int chain_env = [] { const char* e = getenv("PCREG_WALK_CHAIN"); return e ? atoi(e) : 0; }();
     a.chain = chain_env > 0 ? chain_env : WALK_CHAIN;
-    a.fetch_batch = fb_env > 0 ? fb_env : GRID_FETCH_BATCH; a.chunk = ch_env > 0 ? ch_env : GRID_CHUNK;
+    a.fetch_batch = std::min(32, fb_env > 0 ? fb_env : GRID_FETCH_BATCH); a.chunk = std::max(1, ch_env > 0 ? ch_env : GRID_CHUNK);
     PCREG_REQUIRE(a.nq > 0, "nn_grid: no queries");
     PCREG_REQUIRE(a.nq < 2147483647LL, "nn_grid: too many queries in one launch");
     PCREG_REQUIRE(!cl || (int64_t)cl->cap * a.nq < ((int64_t)1 << 40), "nn_grid: candidate lists too large");
@@ -1047,6 +999,22 @@ void nn_grid_launch(const pcreg_model* m, const double* d_sx, const double* d_sy
     static const int wcap_env = [] { const char* e = getenv("PCREG_WALK_CAP"); return e ? atoi(e) : 0; }();
     const int64_t wcap = (int64_t)ctx().sm_count * (wcap_env > 0 ? wcap_env : 256);
     const int walk_blocks = (int)std::min<int64_t>(blocks, wcap);
+    if (m->has_vox && !cl) {
+        // Voronoi voxel map (nn_vox.cu): one list scan per query; the few queries whose voxel has no list (or that lie outside
+        // the padded box) are walked, warm-started by the previous correspondence when there is one.
+        a.vox = m->vox;
+        if (sc.worklist.n < (size_t)a.nq) sc.worklist.alloc((size_t)a.nq);
+        if (sc.count.n < 2) sc.count.alloc(2);
+        PCREG_CUDA(cudaMemsetAsync(sc.count.p, 0, 2 * sizeof(unsigned int), st));
+        a.worklist = sc.worklist.p; a.work_count = sc.count.p;
+        mark(0);
+        nn_vox_launch(m, a, st);
+        mark(2);
+        k_nn_grid_walk<false><<<(int)std::min<int64_t>(blocks, (int64_t)ctx().sm_count * 16), 128, 0, st>>>(a);
+        PCREG_LAUNCHED();
+        mark(3);
+        return;
+    }
     if (d_prev) {
         if (sc.worklist.n < (size_t)a.nq) sc.worklist.alloc((size_t)a.nq);
         if (sc.count.n < 2) sc.count.alloc(2);

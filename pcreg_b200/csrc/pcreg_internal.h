@@ -132,6 +132,19 @@ struct CandView {               // passed by value to kernels
     float build_max_delta;
 };
 
+// Voronoi voxel map (nn_vox.cu): for every voxel of a uniform grid over the padded model bounding box, a
+// conservative superset of the model points that are the nearest neighbour of SOME location inside the voxel.
+// A query reads the short list of its voxel (FP32 offsets from the voxel centre, contiguous) and decides in FP64.
+struct VoxView {                // passed by value to kernels
+    const float4* ent;          // entries: (p - voxel centre) rounded to FP32, w = bits of the int32 position into GridView::pts
+    const uint2* hdr;           // [brick-ordered voxels] x = first entry, y = entries (0: no list -> pyramid walk)
+    int32_t dims[3];            // voxels per axis
+    int32_t tiles[3];           // 4 x 4 x 4 bricks per axis (storage order of hdr)
+    double origin[3];           // lower corner of voxel (0,0,0)
+    double s, inv_s;            // voxel edge
+    float band_abs;             // absolute term of the FP32 error band of the list scan
+};
+
 }  // namespace pcreg
 
 struct pcreg_model {
@@ -150,6 +163,13 @@ struct pcreg_model {
     pcreg::DevBuf<int32_t> g_cell_start;
     std::vector<pcreg::DevBuf<uint8_t>> g_masks;
     int64_t g_occupied = 0;
+    // Voronoi voxel map (built on top of the grid's sorted point array)
+    bool has_vox = false;
+    pcreg::VoxView vox{};
+    pcreg::DevBuf<float4> v_ent;
+    pcreg::DevBuf<uint2> v_hdr;
+    int64_t v_voxels = 0, v_listed = 0, v_entries = 0, v_too_long = 0, v_no_room = 0, v_max_len = 0;
+    double v_build_ms = 0.0;
 };
 
 namespace pcreg {
@@ -223,6 +243,11 @@ void local_points_device(const pcreg_model* m, const double* centres, int64_t nc
                          int64_t max_points, LocalPointsDev& out, cudaStream_t st);
 
 void grid_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st);
+// Voronoi voxel map on top of the grid (nn_vox.cu); leaves m->has_vox false when the model is too dense for the budget
+void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st);
+struct GridArgs;
+// list scan of every query's voxel; queries without a list are appended to a.worklist (then walked by nn_grid.cu)
+void nn_vox_launch(const pcreg_model* m, const GridArgs& a, cudaStream_t st);
 // Upload of a column-major host matrix (ncols columns of `rows` doubles, column stride ld_src) from PAGEABLE memory
 // into a device matrix with column stride ld_dst: columns are packed into two alternating pinned bounce buffers and
 // sent asynchronously, so the host-side packing of one chunk overlaps the DMA of the previous one (a plain

@@ -36,13 +36,13 @@ def test_binding_table_matches_header(built):
     from pcreg_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.pcreg_abi_version() == 1
+    assert lib.pcreg_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     """ctypes mirrors of the POD option structs have the C layout (sizes on x86-64 LP64)."""
     from pcreg_b200 import _lib
-    assert C.sizeof(_lib.ModelOpts) == 40
+    assert C.sizeof(_lib.ModelOpts) == 72
     assert C.sizeof(_lib.AlignOpts) == 48
     assert C.sizeof(_lib.RansacOpts) == 24
     assert C.sizeof(_lib.IcpOpts) == 40

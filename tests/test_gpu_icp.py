@@ -54,7 +54,7 @@ def _problem(nm, ns, H, seed, sigma=0.3, max_deg=8.0):
     return model, src, T0, T_gt
 
 
-@pytest.mark.parametrize("nn", ["brute", "grid"])
+@pytest.mark.parametrize("nn", ["brute", "grid", "grid-novox"])
 @pytest.mark.parametrize("mode", ["plain", "knn", "weighted"])
 def test_icp_modes_match_oracle(pcreg, mode, nn):
     model, src, T0, _ = _problem(20_000, 700, 6, 100)
@@ -64,7 +64,7 @@ def test_icp_modes_match_oracle(pcreg, mode, nn):
     gmode = dict(plain=pcreg.ICP_PLAIN, knn=pcreg.ICP_KNN, weighted=pcreg.ICP_WEIGHTED)[mode]
     thd = 9.0 if mode == "plain" else 0.0
     ref = oracle.icp_batch(model, src, T0, mode=omode, iters=12, k_frac=0.85, R_w=3.5, thDist2=thd, w_src=w_src, return_hist=True)
-    m = pcreg.Model(model, grid=True)
+    m = pcreg.Model(model, grid=True, voxel_map=-1 if nn == "grid-novox" else 0)
     res = pcreg.icp_batch(m, src, T0, mode=gmode, iters=12, k_frac=0.85, R_w=3.5, thDist2=thd, w_src=w_src,
                           nn=pcreg.NN_BRUTE if nn == "brute" else pcreg.NN_GRID, return_idx=True, return_hist=True)
     _compare(res, ref)
@@ -173,7 +173,7 @@ def test_icp_candidate_lists_are_exact_and_used(pcreg):
     model = synth.make_model(150_000, 2024)
     src, T_gt, c = synth.make_source(model, 2500, 0.3, 2025)
     T0 = synth.pose_grid(T_gt, c, 4, (2, 2, 2), 8.0, 1.5, 9)
-    m = pcreg.Model(model, grid=True)
+    m = pcreg.Model(model, grid=True, voxel_map=-1)          # per-query lists are the path of models WITHOUT a voxel map
     pcreg.set_profiling(True)
     a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=30, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
     prof = pcreg.last_profile()
@@ -185,13 +185,14 @@ def test_icp_candidate_lists_are_exact_and_used(pcreg):
     m.destroy()
 
 
-def test_icp_chunked_hypotheses_identical(pcreg, monkeypatch):
+@pytest.mark.parametrize("vm", [-1, 1])
+def test_icp_chunked_hypotheses_identical(pcreg, monkeypatch, vm):
     """Large batches are processed in chunks of hypotheses (bounded scratch: correspondences, candidate lists, the
     extension pool are per chunk).  Forcing 5 hypotheses per chunk must not change a single bit."""
     model = synth.make_model(60_000, 77)
     src, T_gt, c = synth.make_source(model, 1200, 0.3, 78)
     T0 = synth.pose_grid(T_gt, c, 4, (2, 2, 2), 8.0, 1.5, 9)[:23]
-    m = pcreg.Model(model, grid=True)
+    m = pcreg.Model(model, grid=True, voxel_map=vm)
     a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
     monkeypatch.setenv("PCREG_MAX_CHUNK_HYP", "5")
     b = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
@@ -210,7 +211,7 @@ def test_icp_wide_balls_use_extension_lists(pcreg):
     g = synth.rng(33)
     src = np.vstack([src, src[:300] + g.normal(0, 2.5, (300, 3))])          # 17 % gross outliers, 2-6 mm off the surface
     T0 = synth.pose_grid(T_gt, c, 2, (2, 2, 1), 5.0, 1.0, 9)
-    m = pcreg.Model(model, grid=True)
+    m = pcreg.Model(model, grid=True, voxel_map=-1)
     pcreg.set_profiling(True)
     a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=25, nn=pcreg.NN_GRID, return_idx=True)
     prof = pcreg.last_profile()
@@ -224,15 +225,15 @@ def test_icp_wide_balls_use_extension_lists(pcreg):
     m.destroy()
 
 
-@pytest.mark.parametrize("nn", ["brute", "grid"])
+@pytest.mark.parametrize("nn", ["brute", "grid", "grid-novox"])
 def test_icp_two_lanes_identical(pcreg, monkeypatch, nn):
     """Large batches run as two sub-batches on two streams (icp.cu: lanes).  Forcing the two-lane schedule on a small
     batch -- with an odd hypothesis count and several chunks per lane -- must not change a single bit."""
     model = synth.make_model(60_000, 91)
     src, T_gt, c = synth.make_source(model, 1100, 0.3, 92)
     T0 = synth.pose_grid(T_gt, c, 4, (2, 2, 2), 8.0, 1.5, 9)[:27]
-    m = pcreg.Model(model, grid=True)
-    kind = pcreg.NN_GRID if nn == "grid" else pcreg.NN_BRUTE
+    m = pcreg.Model(model, grid=True, voxel_map=-1 if nn == "grid-novox" else 0)
+    kind = pcreg.NN_GRID if nn.startswith("grid") else pcreg.NN_BRUTE
     monkeypatch.setenv("PCREG_LANES", "1")
     a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=12, nn=kind, return_idx=True, return_hist=True)
     monkeypatch.setenv("PCREG_LANES", "2")
@@ -255,7 +256,7 @@ def test_icp_warp_row_scan_identical(pcreg, monkeypatch, mode, cpp):
     model = synth.make_model(80_000, 191)
     src, T_gt, c = synth.make_source(model, 1500, 0.3, 192)
     T0 = synth.pose_grid(T_gt, c, 3, (2, 2, 2), 8.0, 1.5, 19)[:21]
-    m = pcreg.Model(model, grid=True, cells_per_point=cpp)
+    m = pcreg.Model(model, grid=True, cells_per_point=cpp, voxel_map=-1)
     kw = dict(knn=dict(mode=pcreg.ICP_KNN), weighted=dict(mode=pcreg.ICP_WEIGHTED, R_w=3.5),
               reject=dict(mode=pcreg.ICP_PLAIN, thDist2=4.0))[mode]
     ref = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True, **kw)

@@ -11,15 +11,17 @@ pytestmark = pytest.mark.gpu
 
 
 def _check(pcreg, model, q, grid_kw=None):
+    """brute force, the grid kernels (voxel_map=-1) and the Voronoi voxel map (forced: voxel_map=1) against the oracle"""
     oi, od = oracle.nn_brute(model, q)
-    m = pcreg.Model(model, grid=True, **(grid_kw or {}))
-    for kind in (pcreg.NN_BRUTE, pcreg.NN_GRID):
-        gi, gd = m.nn_search(q, kind)
-        bad = np.nonzero(gi != oi)[0]
-        assert bad.size == 0, "kind %d: %d index mismatches, first at %s: got %s want %s (d2 %s vs %s)" % (
-            kind, bad.size, bad[:5], gi[bad[:5]], oi[bad[:5]], gd[bad[:5]], od[bad[:5]])
-        assert np.array_equal(gd, od), "kind %d: d2 not bit-exact (max rel %g)" % (kind, np.max(np.abs(gd - od) / od))
-    m.destroy()
+    for vm in (-1, 1):
+        m = pcreg.Model(model, grid=True, voxel_map=vm, **(grid_kw or {}))
+        for kind in ((pcreg.NN_BRUTE, pcreg.NN_GRID) if vm < 0 else (pcreg.NN_GRID,)):
+            gi, gd = m.nn_search(q, kind)
+            bad = np.nonzero(gi != oi)[0]
+            assert bad.size == 0, "kind %d (voxel_map %d): %d index mismatches, first at %s: got %s want %s (d2 %s vs %s)" % (
+                kind, vm, bad.size, bad[:5], gi[bad[:5]], oi[bad[:5]], gd[bad[:5]], od[bad[:5]])
+            assert np.array_equal(gd, od), "kind %d (voxel_map %d): d2 not bit-exact (max rel %g)" % (kind, vm, np.max(np.abs(gd - od) / od))
+        m.destroy()
 
 
 def test_nn_surface_model_single(pcreg):
