@@ -475,7 +475,7 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         const unsigned long long nvox_l = (unsigned long long)ld[l][0] * ld[l][1] * ld[l][2];
         if (is_top) cap = std::min<unsigned long long>(nvox_l * std::min<unsigned long long>((unsigned long long)n, maxlen_of(l)),
                                                        std::max<unsigned long long>(64ull * (unsigned long long)n, 1ull << 26));
-        else        cap = std::min<unsigned long long>(8ull * used, std::max<unsigned long long>(3ull * used, 1ull << 24));
+        else        cap = 8ull * used + 65536ull * (unsigned long long)VOX_CHUNK;     // a child's list is a subset of its parent's: 8 x is the worst case (+ chunk tails)
         if (fin) cap = std::min<unsigned long long>(cap, (unsigned long long)(budget_bytes / sizeof(float4)));
         cap = std::min<unsigned long long>(std::max<unsigned long long>(cap, 1024ull), 0xfffffff0ull);
         if (fin) ent.alloc((size_t)cap); else c_ids.alloc((size_t)cap);
