@@ -492,8 +492,9 @@ def icp_batch(model: Model, src, T0s, mode=ICP_PLAIN, iters=50, k_frac=0.85, R_w
     return out
 
 
-def set_profiling(enabled: bool):
-    L.check(L.lib().pcreg_set_profiling(int(bool(enabled))), "pcreg_set_profiling")
+def set_profiling(enabled):
+    """True / 1: event times + work counters; 2: event times only (no counter atomics in the kernels); False: off."""
+    L.check(L.lib().pcreg_set_profiling(int(enabled)), "pcreg_set_profiling")
 
 
 def last_profile() -> dict:
@@ -507,7 +508,7 @@ def last_profile() -> dict:
                 list_entries_read=v[13], list_points_gathered=v[14],
                 rowscan_points=v[7], rowscan_rows=v[8], walk_points=v[15], walk_leaves=v[16],
                 list_ms=v[17], rowscan_ms=v[18], walk_ms=v[19], list_launches=v[20], rowscan_launches=v[21], walk_launches=v[22],
-                match_score_ms=v[24], match_terms=v[25], voxel_map=v[26])
+                match_score_ms=v[24], match_terms=v[25], voxel_map=v[26], fused=v[27])
 
 
 def launch_count() -> int:

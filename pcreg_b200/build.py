@@ -15,12 +15,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpcreg_b200.so")
-OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["model.cu", "nn_brute.cu", "nn_grid.cu", "nn_vox.cu", "icp.cu", "kabsch_ransac.cu", "align.cu", "local_points.cu", "descriptor.cu", "match.cu"]
-HEADERS = ["pcreg_internal.h", "pcreg_dev.cuh", "pcreg_math.cuh", "pcreg_select.cuh", "pcreg_grid.cuh", os.path.join("..", "..", "include", "pcreg.h")]
+# PCREG_LIB_OUT / PCREG_NVCC_EXTRA: build a VARIANT of the library (other output file, extra nvcc flags such as -DUPD_THREADS_OVERRIDE=384)
+# for same-session A/B timing with PCREG_LIB=<variant>; the default build ignores both
+LIB = os.environ.get("PCREG_LIB_OUT") or os.path.join(HERE, "libpcreg_b200.so")
+OBJDIR = os.path.join(HERE, "build" if not os.environ.get("PCREG_LIB_OUT") else "build_" + os.path.basename(os.environ["PCREG_LIB_OUT"]))
+SOURCES = ["model.cu", "nn_brute.cu", "nn_grid.cu", "nn_vox.cu", "icp.cu", "icp_fused.cu", "kabsch_ransac.cu", "align.cu", "local_points.cu", "descriptor.cu", "match.cu"]
+HEADERS = ["pcreg_internal.h", "pcreg_dev.cuh", "pcreg_math.cuh", "pcreg_select.cuh", "pcreg_grid.cuh", "pcreg_vox.cuh", "pcreg_icp.cuh", os.path.join("..", "..", "include", "pcreg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"] + os.environ.get("PCREG_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -20,15 +20,15 @@
 
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
+#include "pcreg_grid.cuh"
 #include "pcreg_select.cuh"
 #include "pcreg_math.cuh"
+#include "pcreg_icp.cuh"
 
 namespace pcreg {
 
-constexpr int UPD_THREADS = 256;
-
 // One block per hypothesis.
-__global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
+__global__ void __launch_bounds__(UPD_THREADS, 1) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
     __shared__ double Ts[16];
     __shared__ double red[KABSCH_NSUMS * 32];
     __shared__ long long redll[32];
@@ -131,17 +131,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_cons
             if (w > 0.0) ++n_used;
             double qx, qy, qz;
             quick_tf(Ts, xs[u], ys[u], zs[u], qx, qy, qz);
-            const ModelPointD m = mm[u];
-            const double q0 = qx - px, q1 = qy - py, q2 = qz - pz;
-            const double m0 = m.x - px, m1 = m.y - py, m2 = m.z - pz;
-            const double wq0 = w * q0, wq1 = w * q1, wq2 = w * q2;
-            s[0] += w;
-            s[1] += wq0; s[2] += wq1; s[3] += wq2;
-            s[4] += w * m0; s[5] += w * m1; s[6] += w * m2;
-            s[7] += wq0 * m0; s[8] += wq0 * m1; s[9] += wq0 * m2;
-            s[10] += wq1 * m0; s[11] += wq1 * m1; s[12] += wq1 * m2;
-            s[13] += wq2 * m0; s[14] += wq2 * m1; s[15] += wq2 * m2;
-            s[16] += w * d;
+            icp_accumulate(s, w, d, qx, qy, qz, mm[u], px, py, pz);
         }
     }
     block_sum<KABSCH_NSUMS>(s, red);
@@ -155,18 +145,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) k_icp_update(const __grid_cons
         if (a.rmse_hist) a.rmse_hist[h * a.hist_stride + a.hist_col] = rmse;
         float moved = 0.f;
         if (a.update && !a.frozen[h]) {
-            if (n_used < 3 || !(sw > 0.0)) {
+            double Tn[16], Tc[16];
+            for (int k = 0; k < 16; ++k) Tc[k] = Ts[k];
+            if (!icp_pose_update(s, n_used, a.pivot, a.reflection_fix != 0, Tc, Tn)) {
                 a.frozen[h] = 1;
             } else {
-                KabschSums ks;
-                ks.sw = sw;
-                for (int k = 0; k < 3; ++k) { ks.sq[k] = s[1 + k]; ks.sm[k] = s[4 + k]; }
-                for (int k = 0; k < 9; ++k) ks.sqm[k] = s[7 + k];
-                ks.swd2 = s[16];
-                double dT[16], Tn[16], Tc[16];
-                kabsch_from_sums(ks, a.pivot, a.pivot, a.reflection_fix != 0, dT);
-                for (int k = 0; k < 16; ++k) Tc[k] = Ts[k];
-                mul4(Tc, dT, Tn);
                 for (int k = 0; k < 16; ++k) a.T[h * 16 + k] = Tn[k];
                 if (a.delta) {
                     // upper bound of how far this update moves any source point:
@@ -390,6 +373,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     const double t_enter = now_ms();
     double t_alloc = 0, t_sorted = 0, t_enq = 0;
 
+    const bool fused = icp_fused_eligible(m, ns, o);
     // chunk the hypotheses so that the per-correspondence scratch stays bounded
     const size_t total_b = c.total_mem;         // queried once at pcreg_init (cudaMemGetInfo costs up to tens of ms per call)
     const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + (m->has_vox ? 0 : 28 + 4 * 64 + 4 * 448 / 16) : 0));
@@ -444,7 +428,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
         int64_t h0 = 0, hn = 0;
     };
     Lane lanes[MAX_LANES];
-    for (int l = 0; l < nlanes; ++l) {
+    for (int l = 0; l < nlanes && !fused; ++l) {
         Lane& L = lanes[l];
         L.st = (nlanes == 1) ? st : lane_stream(l);
         L.idxA.alloc((size_t)hc * ns); L.idxB.alloc((size_t)hc * ns); L.d2.alloc((size_t)hc * ns);
@@ -493,6 +477,38 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     }
     t_sorted = now_ms();
     const double* sx = d_src; const double* sy = d_src + ns; const double* sz = d_src + 2 * ns;
+    if (fused) {
+        // One launch for the whole batch: each block runs every pass of one hypothesis (icp_fused.cu).
+        FusedArgs fa{};
+        fa.g.g = m->grid; fa.g.md = m->md.p; fa.g.vox = m->vox;
+        fa.sx = sx; fa.sy = sy; fa.sz = sz; fa.w_src = d_w; fa.ns = (int32_t)ns;
+        for (int k = 0; k < 3; ++k) fa.pivot[k] = m->pivot[k];
+        fa.T = Twork.p; fa.frozen = frozen.p; fa.rmse = rm; fa.n_used = nu;
+        fa.rmse_hist = d_rmse_hist; fa.hist_stride = o.iters + 1;
+        fa.idx_out = d_idx; fa.perm = sorted ? sperm.p : nullptr; fa.tie_order = sorted ? sinv.p : nullptr;
+        fa.mode = o.mode; fa.k_frac = o.k_frac; fa.R_w = o.R_w; fa.thDist2 = o.thDist2; fa.reflection_fix = o.reflection_fix; fa.iters = o.iters;
+        fa.counters = (prof && c.profiling_counters) ? counters.p : nullptr;
+        ev_begin(0);
+        icp_fused_launch(fa, nhyp, st);
+        ev_end();
+        transpose16_launch(Twork.p, d_T16_cm, nhyp, st);
+        if (d_status) PCREG_CUDA(cudaMemcpyAsync(d_status, frozen.p, (size_t)nhyp * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        if (d_best) icp_argmin_launch(rm, nhyp, d_best, st);
+        PCREG_CUDA(cudaStreamSynchronize(st));
+        if (prof) {
+            float ms = 0.f;
+            PCREG_CUDA(cudaEventElapsedTime(&ms, evs[0].a, evs[0].b));
+            unsigned long long hcnt[16] = {0};
+            PCREG_CUDA(cudaMemcpy(hcnt, counters.p, sizeof hcnt, cudaMemcpyDeviceToHost));
+            const double nq = (double)nhyp * (double)ns * (double)(o.iters + 1);
+            c.profile[0] = 1; c.profile[1] = ms; c.profile[2] = nq; c.profile[6] = nq;
+            c.profile[11] = (double)hcnt[4]; c.profile[10] = nq - (double)hcnt[4];
+            c.profile[13] = (double)hcnt[6]; c.profile[14] = (double)hcnt[7];
+            c.profile[17] = ms; c.profile[20] = 1;
+            c.profile[26] = 1.0; c.profile[27] = 1.0;
+        }
+        return;
+    }
     k_src_stats<<<1, 1024, 0, st>>>(d_src, ns, src_stats.p);
     PCREG_LAUNCHED();
     if (use_lists) {
@@ -542,7 +558,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
                     nn_brute_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, L.have_prev ? L.prev : nullptr, out_idx, L.d2.p, L.scratch, ls);
                 else
                     nn_grid_launch(m, sx, sy, sz, ns, Twork.p + h0 * 16, hn, L.have_prev ? L.prev : nullptr, out_idx, L.d2.p,
-                                   prof ? counters.p : nullptr, L.gscratch, use_lists ? &L.cl : nullptr, it >= 2,
+                                   (prof && c.profiling_counters) ? counters.p : nullptr, L.gscratch, use_lists ? &L.cl : nullptr, it >= 2,
                                    (lazy_trim && it >= 2 && !last) ? skip_thr.p + h0 : nullptr, ls);
                 ev_end();
                 nn_launches += 1;
@@ -711,7 +727,7 @@ int pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t 
         nn_brute_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p, scratch, st);
     else
         nn_grid_launch(m, d_q.p, d_q.p + nq, d_q.p + 2 * nq, nq, d_T.p, 1, nullptr, d_idx.p, d_d2.p,
-                       c.profiling ? counters.p : nullptr, gscratch, nullptr, false, nullptr, st);
+                       (c.profiling && c.profiling_counters) ? counters.p : nullptr, gscratch, nullptr, false, nullptr, st);
     if (c.profiling) PCREG_CUDA(cudaEventRecord(e1, st));
     PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
     if (d2) PCREG_CUDA(cudaMemcpyAsync(d2, d_d2.p, d_d2.bytes(), cudaMemcpyDeviceToHost, st));

@@ -433,7 +433,7 @@ int pcreg_shutdown(void) {
     return PCREG_OK;
 }
 
-int pcreg_set_profiling(int enabled) { ctx().profiling = enabled != 0; return PCREG_OK; }
+int pcreg_set_profiling(int enabled) { ctx().profiling = enabled != 0; ctx().profiling_counters = enabled != 2; return PCREG_OK; }
 int pcreg_last_profile(double out[32]) {
     if (!out) return PCREG_ERR_ARG;
     for (int i = 0; i < 32; ++i) out[i] = ctx().profile[i];

@@ -43,88 +43,6 @@
 
 namespace pcreg {
 
-constexpr int GRID_STACK = 80;
-// depth-first walk: starts from the root (1 entry, GRID_MAX_LEVELS - 1 levels to descend) or from <= 8 nodes below it;
-// every expanded node replaces itself by at most 8 children (net +7 per level)
-static_assert(1 + 7 * (GRID_MAX_LEVELS - 1) <= GRID_STACK && 8 + 7 * (GRID_MAX_LEVELS - 2) <= GRID_STACK,
-              "k_nn_grid_walk: explicit stack too small for GRID_MAX_LEVELS");
-constexpr float GRID_SLOP_ABS = 1.3e-4f;   // cell units: FP32 rounding of the query (<= 1024 cells) + of the difference
-constexpr float GRID_SLOP_REL = 2.5e-7f;
-
-// stack entry: [63:34] lower bound (positive float, lowest mantissa bit dropped = rounded down),
-//              [33:30] level, [29:20] z, [19:10] y, [9:0] x
-__device__ __forceinline__ unsigned long long pack_entry(float lb, int level, int x, int y, int z) {
-    return ((unsigned long long)(__float_as_uint(lb) >> 1) << 34) | ((unsigned long long)(unsigned)level << 30) |
-           ((unsigned long long)(unsigned)z << 20) | ((unsigned long long)(unsigned)y << 10) | (unsigned long long)(unsigned)x;
-}
-
-// conservative (never too large) distance along one axis, in cell units, from q to the slab [lo, lo+edge]
-__device__ __forceinline__ float axis_lb(float q, float lo, float edge) {
-    const float d = fmaxf(lo - q, q - (lo + edge));
-    return fmaxf(fmaf(-GRID_SLOP_REL, fabsf(d), d) - GRID_SLOP_ABS, 0.f);
-}
-// conservative squared distance, in cell units, from the query to the box [x, x+1] * edge (corners exact in FP32)
-__device__ __forceinline__ float box_lb(float qx, float qy, float qz, int x, int y, int z, float edge) {
-    const float dx = axis_lb(qx, (float)x * edge, edge), dy = axis_lb(qy, (float)y * edge, edge), dz = axis_lb(qz, (float)z * edge, edge);
-    return (dx * dx + dy * dy + dz * dz) * (1.f - 6e-7f);
-}
-// guaranteed upper bound of best (squared distance) in squared cell units, as a float
-__device__ __forceinline__ float best_ub_cells(double best, double inv_cell2) {
-    const double b = best * inv_cell2;
-    return (b < 3.0e38) ? __double2float_ru(b) * (1.f + 6e-7f) : FLT_MAX;
-}
-// same for the ball of radius (sqrt(best) + gap): everything inside it gets visited
-__device__ __forceinline__ float best_ub_cells_gap(double best, double inv_cell, float gap_cells) {
-    const double r = sqrt(best) * inv_cell + (double)gap_cells;
-    const double b = r * r;
-    return (b < 3.0e38) ? __double2float_ru(b) * (1.f + 6e-7f) : FLT_MAX;
-}
-
-struct Query {
-    double qx, qy, qz;      // FP64 query (oracle order)
-    float fx, fy, fz;       // in cell units, FP32 (pruning only)
-    double best; int32_t bidx; float bestc;
-    int ilx, ihx, ily, ihy, ilz, ihz;   // level-0 cell span of the ball's bounding cube (valid when has_span)
-    bool has_span;
-};
-
-__device__ __forceinline__ void setup_query(const GridArgs& a, int64_t gq, Query& Q, float gap_cells, int32_t warm) {
-    const GridView& G = a.g;
-    const unsigned h = (unsigned)gq / (unsigned)a.ns, i = (unsigned)gq - h * (unsigned)a.ns;      // nq < 2^31 (launcher)
-    quick_tf(a.T + (size_t)h * 16, a.sx[i], a.sy[i], a.sz[i], Q.qx, Q.qy, Q.qz);
-    Q.fx = __double2float_rn((Q.qx - G.origin[0]) * G.inv_cell);
-    Q.fy = __double2float_rn((Q.qy - G.origin[1]) * G.inv_cell);
-    Q.fz = __double2float_rn((Q.qz - G.origin[2]) * G.inv_cell);
-    Q.best = INFINITY;
-    Q.bidx = -1;
-    if (warm >= 0) {                 // any model point bounds the answer: the caller's previous correspondence, or a neighbour's
-        const ModelPointD mp = a.md[warm];
-        Q.best = dist2_exact(mp.x, mp.y, mp.z, Q.qx, Q.qy, Q.qz);
-        Q.bidx = warm;
-    }
-    Q.bestc = (gap_cells > 0.f) ? best_ub_cells_gap(Q.best, G.inv_cell, gap_cells) : best_ub_cells(Q.best, G.inv_cell * G.inv_cell);
-    Q.has_span = false;
-    if (Q.bidx >= 0 && Q.bestc < 1.0e12f) {
-        // ball radius in cells (upper bound) -> integer cell span
-        const float rc = __fsqrt_ru(Q.bestc) + 2.0f * GRID_SLOP_ABS + GRID_SLOP_REL * (fabsf(Q.fx) + fabsf(Q.fy) + fabsf(Q.fz));
-        const float big = 1.0e6f;
-        Q.ilx = (int)floorf(fmaxf(fminf(Q.fx - rc, big), -big)); Q.ihx = (int)floorf(fmaxf(fminf(Q.fx + rc, big), -big));
-        Q.ily = (int)floorf(fmaxf(fminf(Q.fy - rc, big), -big)); Q.ihy = (int)floorf(fmaxf(fminf(Q.fy + rc, big), -big));
-        Q.ilz = (int)floorf(fmaxf(fminf(Q.fz - rc, big), -big)); Q.ihz = (int)floorf(fmaxf(fminf(Q.fz + rc, big), -big));
-        Q.has_span = true;
-    }
-}
-
-__device__ __forceinline__ void scan_points(const GridView& G, int32_t s0, int32_t s1, Query& Q, double inv_cell2) {
-    bool improved = false;
-    for (int32_t p = s0; p < s1; ++p) {
-        const GridPoint gp = G.pts[p];
-        const double d = dist2_exact(gp.x, gp.y, gp.z, Q.qx, Q.qy, Q.qz);
-        if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) { Q.best = d; Q.bidx = gp.orig; improved = true; }
-    }
-    if (improved) Q.bestc = best_ub_cells(Q.best, inv_cell2);
-}
-
 // ---- kernel 1: row scan ----------------------------------------------------------------------------------
 // Cells of one x-row are contiguous in memory, so for a fixed (y,z) the cells the ball can touch are ONE
 // run of points [cell_start[row + xa], cell_start[row + xb + 1]).  A query whose bounding cube spans at
@@ -140,45 +58,6 @@ constexpr int GRID_ROW_SPAN = 12;
 constexpr int GRID_FETCH_BATCH = 8;
 constexpr int GRID_CHUNK = 32;
 constexpr double GRID_WARP_ROWS_DENSITY = 6.0;      // model points per occupied cell from which the warp-per-query row scan is used
-
-// (sqrt(best) + skin)^2, never too small: the points with d2 <= this value enter the candidate list
-__device__ __forceinline__ double list_thr2(double best, double skin) {
-    const double t = sqrt(best) + skin;
-    return t * t * (1.0 + 1e-12);
-}
-// append grid position p to the list under construction: the first cl.cap entries live in the query's own
-// row, longer lists (wide balls) continue in an extension slot taken from a shared pool on first need
-// entry = position << 8 | level, level = where sqrt(d2) falls in [lo, lo + 2 skin] on a 256-step scale, rounded DOWN by
-// a whole step (the scan skips an entry only if even the lower edge of its level is out of reach)
-__device__ __forceinline__ void list_append(const CandView& cl, int64_t gq, int& lc, int& ext_slot, int32_t pos, double d, float lo) {
-    const float sd = __fsqrt_rd(__double2float_rd(d));
-    const int level = min(max((int)floorf((sd - lo) * cl.inv_level) - 1, 0), 255);
-    const int32_t p = (int32_t)(((unsigned)pos << 8) | (unsigned)level);
-    if (lc < cl.cap) {
-        cl.list[gq * cl.cap + lc] = p;
-    } else {
-        if (ext_slot == -1) {
-            const unsigned s = atomicAdd(cl.ext_count, 1u);
-            ext_slot = s < (unsigned)cl.ext_slots ? (int)s : -2;          // -2: pool exhausted
-        }
-        const int k = lc - cl.cap;
-        if (ext_slot >= 0 && k < cl.ext_cap) cl.ext_list[(int64_t)ext_slot * cl.ext_cap + k] = p;
-    }
-    ++lc;
-}
-// close the list of a finished search: header + count, or "no list"
-__device__ __forceinline__ void list_commit(const CandView& cl, const GridView& G, int64_t gq, const Query& Q, bool bld, int lc, int ext_slot, float lo) {
-    if (ext_slot >= 0) cl.ext[gq] = ext_slot;
-    if (bld && lc > 0 && (lc <= cl.cap || (ext_slot >= 0 && lc <= cl.cap + cl.ext_cap))) {
-        // every model point within R_list of this position is in the list
-        const double rl = (sqrt(Q.best) + cl.skin) * (1.0 - 1e-7);
-        cl.hdr[gq] = make_float4(__double2float_rn(Q.qx - G.origin[0]), __double2float_rn(Q.qy - G.origin[1]),
-                                 __double2float_rn(Q.qz - G.origin[2]), __double2float_rd(rl));
-        cl.cnt[gq] = make_int2(lc, __float_as_int(lo));
-    } else {
-        cl.cnt[gq] = make_int2(-1, 0);
-    }
-}
 
 template <bool BUILD>
 __global__ void __launch_bounds__(128, 8) k_nn_grid_direct(const __grid_constant__ GridArgs a) {
@@ -650,87 +529,7 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
                 ext_slot = a.cl.ext[gq]; thr2 = list_thr2(Q.best, a.cl.skin);
                 lo = __fsqrt_rd(__double2float_rd(Q.best)) - (float)a.cl.skin;
             }
-            const float fx = Q.fx, fy = Q.fy, fz = Q.fz;
-            unsigned long long stack[GRID_STACK];
-            int sp = 0;
-            const int top = G.nlevels - 1;
-            bool from_root = true;
-            if (Q.has_span) {
-                // lowest level whose <= 2 x 2 x 2 nodes cover the ball's bounding cube
-                int l = 0;
-                while (l < top && (((Q.ihx >> l) - (Q.ilx >> l)) > 1 || ((Q.ihy >> l) - (Q.ily >> l)) > 1 || ((Q.ihz >> l) - (Q.ilz >> l)) > 1)) ++l;
-                if (((Q.ihx >> l) - (Q.ilx >> l)) <= 1 && ((Q.ihy >> l) - (Q.ily >> l)) <= 1 && ((Q.ihz >> l) - (Q.ilz >> l)) <= 1) {
-                    from_root = false;
-                    const float edge = (float)(1 << l);
-                    const int dxl = G.dims[l][0], dyl = G.dims[l][1], dzl = G.dims[l][2];
-                    for (int z = Q.ilz >> l; z <= (Q.ihz >> l); ++z) {
-                        if (z < 0 || z >= dzl) continue;
-                        for (int y = Q.ily >> l; y <= (Q.ihy >> l); ++y) {
-                            if (y < 0 || y >= dyl) continue;
-                            for (int x = Q.ilx >> l; x <= (Q.ihx >> l); ++x) {
-                                if (x < 0 || x >= dxl) continue;
-                                if (l > 0 && G.mask[l][((int64_t)z * dyl + y) * dxl + x] == 0) continue;
-                                const float lb = box_lb(fx, fy, fz, x, y, z, edge);
-                                if (lb <= Q.bestc) stack[sp++] = pack_entry(lb, l, x, y, z);
-                            }
-                        }
-                    }
-                }
-            }
-            if (from_root) stack[sp++] = pack_entry(0.f, top, 0, 0, 0);
-
-            while (sp > 0) {
-                const unsigned long long e = stack[--sp];
-                const float lbf = __uint_as_float((unsigned)(e >> 34) << 1);
-                if (lbf > Q.bestc) continue;
-                const unsigned lo32 = (unsigned)e;
-                const int level = (int)((e >> 30) & 0xF);
-                const int ix = (int)(lo32 & 1023u), iy = (int)((lo32 >> 10) & 1023u), iz = (int)((lo32 >> 20) & 1023u);
-                ++n_nodes;
-                if (level == 0) {
-                    // exact FP64 scan of the leaf's points
-                    const int64_t c = ((int64_t)iz * G.dims[0][1] + iy) * G.dims[0][0] + ix;
-                    const int32_t s0 = G.cell_start[c], s1 = G.cell_start[c + 1];
-                    ++n_cells;
-                    n_pts += (unsigned long long)(s1 - s0);
-                    bool improved = false;
-                    for (int32_t p = s0; p < s1; ++p) {
-                        const GridPoint gp = G.pts[p];
-                        const double d = dist2_exact(gp.x, gp.y, gp.z, Q.qx, Q.qy, Q.qz);
-                        if (d < Q.best || (d == Q.best && gp.orig < Q.bidx)) {
-                            Q.best = d; Q.bidx = gp.orig; improved = true;
-                            if (BUILD && bld) thr2 = list_thr2(Q.best, a.cl.skin);
-                        }
-                        if (BUILD && bld && d <= thr2) list_append(a.cl, gq, lc, ext_slot, p, d, lo);
-                    }
-                    if (improved) Q.bestc = (BUILD && bld) ? best_ub_cells_gap(Q.best, G.inv_cell, a.cl.gap_cells) : best_ub_cells(Q.best, inv_cell2);
-                    continue;
-                }
-                const int64_t c = ((int64_t)iz * G.dims[level][1] + iy) * G.dims[level][0] + ix;
-                unsigned m = G.mask[level][c];
-                const float edge = (float)(1 << (level - 1));              // child edge in cells
-                // per-axis squared bounds of the two half slabs; a child's bound is one pick per axis
-                const float bx = (float)(2 * ix) * edge, by = (float)(2 * iy) * edge, bz = (float)(2 * iz) * edge;
-                float ax0 = axis_lb(fx, bx, edge), ax1 = axis_lb(fx, bx + edge, edge);
-                float ay0 = axis_lb(fy, by, edge), ay1 = axis_lb(fy, by + edge, edge);
-                float az0 = axis_lb(fz, bz, edge), az1 = axis_lb(fz, bz + edge, edge);
-                ax0 *= ax0; ax1 *= ax1; ay0 *= ay0; ay1 *= ay1; az0 *= az0; az1 *= az1;
-                const unsigned oct = (fx >= bx + edge ? 1u : 0u) | (fy >= by + edge ? 2u : 0u) | (fz >= bz + edge ? 4u : 0u);
-                // permute the mask so that bit t <-> child (t ^ oct); then high bits = far octants
-                if (oct & 1u) m = ((m & 0xAAu) >> 1) | ((m & 0x55u) << 1);
-                if (oct & 2u) m = ((m & 0xCCu) >> 2) | ((m & 0x33u) << 2);
-                if (oct & 4u) m = ((m & 0xF0u) >> 4) | ((m & 0x0Fu) << 4);
-                while (m) {
-                    const int t = 31 - __clz(m);                           // far first, so the near octant is popped first
-                    m &= ~(1u << t);
-                    const int k = t ^ (int)oct;
-                    const float lb = ((((k & 1) ? ax1 : ax0) + ((k & 2) ? ay1 : ay0)) + ((k & 4) ? az1 : az0)) * (1.f - 6e-7f);
-                    if (lb <= Q.bestc) {
-                        if (sp >= GRID_STACK) __trap();            // unreachable (static_assert below): never drop a node silently
-                        stack[sp++] = pack_entry(lb, level - 1, 2 * ix + (k & 1), 2 * iy + ((k >> 1) & 1), 2 * iz + (k >> 2));
-                    }
-                }
-            }
+            walk_search<BUILD>(a, gq, Q, bld, lc, ext_slot, thr2, lo, n_pts, n_cells, n_nodes);
             a.idx[gq] = Q.bidx;
             if (a.d2) a.d2[gq] = Q.best;
             if (BUILD) list_commit(a.cl, G, gq, Q, bld, lc, ext_slot, lo);

@@ -36,6 +36,7 @@
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
 #include "pcreg_grid.cuh"
+#include "pcreg_vox.cuh"
 
 namespace pcreg {
 
@@ -43,20 +44,6 @@ constexpr uint32_t VOX_DROPPED = 0xffffffffu;   // intermediate levels: list dro
 constexpr int VOX_CHUNK = 512;                  // pool entries a warp reserves per atomic
 constexpr int VOX_TOP_DIM = 16;                 // the top level (lists filtered out of ALL points) has at most this many voxels per axis
 constexpr int VOX_BASE_CAP = 64;                // longest list kept at the finest level (x4 per level above)
-
-// hdr arrays are stored in 4 x 4 x 4 bricks: queries of a warp are neighbours in space, so their headers share sectors
-__host__ __device__ __forceinline__ int64_t brick_index(int x, int y, int z, const int32_t* tiles) {
-    const int64_t tile = ((int64_t)(z >> 2) * tiles[1] + (y >> 2)) * tiles[0] + (x >> 2);
-    return (tile << 6) | (int64_t)(((z & 3) << 4) | ((y & 3) << 2) | (x & 3));
-}
-__device__ __forceinline__ void brick_decode(int64_t slot, const int32_t* tiles, int& x, int& y, int& z) {
-    const int64_t tile = slot >> 6;
-    const int in = (int)(slot & 63);
-    const int tx = (int)(tile % tiles[0]), ty = (int)((tile / tiles[0]) % tiles[1]), tz = (int)(tile / ((int64_t)tiles[0] * tiles[1]));
-    x = tx * 4 + (in & 3); y = ty * 4 + ((in >> 2) & 3); z = tz * 4 + (in >> 4);
-}
-// the one formula for a voxel centre (build and query must agree to FP64 rounding)
-__device__ __forceinline__ double vox_centre(double origin, int i, double s) { return __fma_rn((double)i + 0.5, s, origin); }
 
 struct VoxLevelArgs {
     const GridPoint* pts; uint32_t npts;
@@ -344,53 +331,14 @@ __global__ void __launch_bounds__(256) k_nn_vox(const __grid_constant__ GridArgs
         const unsigned h = (unsigned)gq / (unsigned)a.ns, i = (unsigned)gq - h * (unsigned)a.ns;
         double qx, qy, qz;
         quick_tf(a.T + (size_t)h * 16, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
-        const double ux = (qx - V.origin[0]) * V.inv_s, uy = (qy - V.origin[1]) * V.inv_s, uz = (qz - V.origin[2]) * V.inv_s;
-        // (a NaN pose fails these comparisons and goes to the walk, like every query outside the padded box)
-        if (ux >= 0.0 && uy >= 0.0 && uz >= 0.0 && ux < (double)V.dims[0] && uy < (double)V.dims[1] && uz < (double)V.dims[2]) {
-            const int ix = (int)ux, iy = (int)uy, iz = (int)uz;
-            const uint2 hd = V.hdr[brick_index(ix, iy, iz, V.tiles)];
-            if (hd.y == 0u) {
-                defer = true;
-            } else {
-                const float x = __double2float_rn(qx - vox_centre(V.origin[0], ix, V.s));
-                const float y = __double2float_rn(qy - vox_centre(V.origin[1], iy, V.s));
-                const float z = __double2float_rn(qz - vox_centre(V.origin[2], iz, V.s));
-                const float4* __restrict__ L = V.ent + hd.x;
-                float m1 = FLT_MAX, m2 = FLT_MAX;
-                int r1 = 0;
-                for (uint32_t k = 0; k < hd.y; ++k) {
-                    const float4 en = L[k];
-                    const float dx = en.x - x, dy = en.y - y, dz = en.z - z;
-                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(en.w); }
-                    else m2 = fminf(m2, d);
-                }
-                const float thr = fmaf(m1, 3e-6f, m1) + V.band_abs;
-                double best; int32_t bidx;
-                {
-                    const GridPoint gp = a.g.pts[r1];
-                    best = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
-                    bidx = gp.orig;
-                }
-                n_gather = 1;
-                if (m2 <= thr) {                                     // more than one entry inside the FP32 error band: decide in FP64
-                    for (uint32_t k = 0; k < hd.y; ++k) {
-                        const float4 en = L[k];
-                        const float dx = en.x - x, dy = en.y - y, dz = en.z - z;
-                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        const int r = __float_as_int(en.w);
-                        if (d <= thr && r != r1) {
-                            const GridPoint gp = a.g.pts[r];
-                            const double dd = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
-                            if (dd < best || (dd == best && gp.orig < bidx)) { best = dd; bidx = gp.orig; }
-                            ++n_gather;
-                        }
-                    }
-                }
-                a.idx[gq] = bidx;
-                if (a.d2) a.d2[gq] = best;
-                n_read = hd.y; n_done = 1;
-            }
+        uint2 hd;
+        float x, y, z;
+        if (vox_lookup(V, qx, qy, qz, hd, x, y, z)) {
+            int32_t bidx; double best; unsigned ng;
+            vox_scan(V, a.g.pts, hd, x, y, z, qx, qy, qz, bidx, best, ng);
+            a.idx[gq] = bidx;
+            if (a.d2) a.d2[gq] = best;
+            n_read = hd.y; n_gather = ng; n_done = 1;
         } else {
             defer = true;
         }

@@ -55,6 +55,7 @@ struct Context {
     size_t smem_optin = 0;
     size_t total_mem = 0;                // device memory, bytes
     bool profiling = false;
+    bool profiling_counters = true;      // pcreg_set_profiling(2): event times only (the counters add atomics to the kernels)
     double profile[32] = {0};
     std::vector<cudaEvent_t> events;     // reusable timing events (profiling mode)
     std::vector<cudaStream_t> streams;   // internal streams of the two-lane ICP loop

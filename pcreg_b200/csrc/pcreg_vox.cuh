@@ -1,0 +1,84 @@
+// pcreg_vox.cuh -- device side of the Voronoi voxel map (built by nn_vox.cu): voxel addressing and the exact list scan
+// of one query.  Shared by k_nn_vox (one launch per NN pass) and the fused ICP kernel (icp_fused.cu).
+#pragma once
+#include <float.h>
+#include "pcreg_internal.h"
+#include "pcreg_dev.cuh"
+
+namespace pcreg {
+
+// hdr arrays are stored in 4 x 4 x 4 bricks: queries of a warp are neighbours in space, so their headers share sectors
+__host__ __device__ __forceinline__ int64_t brick_index(int x, int y, int z, const int32_t* tiles) {
+    const int64_t tile = ((int64_t)(z >> 2) * tiles[1] + (y >> 2)) * tiles[0] + (x >> 2);
+    return (tile << 6) | (int64_t)(((z & 3) << 4) | ((y & 3) << 2) | (x & 3));
+}
+__device__ __forceinline__ void brick_decode(int64_t slot, const int32_t* tiles, int& x, int& y, int& z) {
+    const int64_t tile = slot >> 6;
+    const int in = (int)(slot & 63);
+    const int tx = (int)(tile % tiles[0]), ty = (int)((tile / tiles[0]) % tiles[1]), tz = (int)(tile / ((int64_t)tiles[0] * tiles[1]));
+    x = tx * 4 + (in & 3); y = ty * 4 + ((in >> 2) & 3); z = tz * 4 + (in >> 4);
+}
+// the one formula for a voxel centre (build and query must agree to FP64 rounding)
+__device__ __forceinline__ double vox_centre(double origin, int i, double s) { return __fma_rn((double)i + 0.5, s, origin); }
+
+// Voxel of q: its list header and q relative to the voxel centre (FP32).  False when the map cannot answer (q outside the
+// padded box -- a NaN pose fails the comparisons too -- or a voxel whose list was dropped): the caller walks the pyramid.
+__device__ __forceinline__ bool vox_lookup(const VoxView& V, double qx, double qy, double qz, uint2& hd, float& x, float& y, float& z) {
+    const double ux = (qx - V.origin[0]) * V.inv_s, uy = (qy - V.origin[1]) * V.inv_s, uz = (qz - V.origin[2]) * V.inv_s;
+    if (!(ux >= 0.0 && uy >= 0.0 && uz >= 0.0 && ux < (double)V.dims[0] && uy < (double)V.dims[1] && uz < (double)V.dims[2])) return false;
+    const int ix = (int)ux, iy = (int)uy, iz = (int)uz;
+    hd = V.hdr[brick_index(ix, iy, iz, V.tiles)];
+    x = __double2float_rn(qx - vox_centre(V.origin[0], ix, V.s));
+    y = __double2float_rn(qy - vox_centre(V.origin[1], iy, V.s));
+    z = __double2float_rn(qz - vox_centre(V.origin[2], iz, V.s));
+    return hd.y != 0u;
+}
+
+// Exact nearest neighbour of q among the entries of its voxel's list: FP32 scan (four entries in flight), then the entries
+// inside the FP32 error band -- normally one -- decided in FP64 with the oracle's formula on (d2, original index).
+__device__ __forceinline__ void vox_scan(const VoxView& V, const GridPoint* __restrict__ pts, uint2 hd, float x, float y, float z,
+                                         double qx, double qy, double qz, int32_t& bidx, double& best, unsigned& n_gather) {
+    const float4* __restrict__ L = V.ent + hd.x;
+    const uint32_t n = hd.y;
+    const float4 far = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
+    float m1 = FLT_MAX, m2 = FLT_MAX;
+    int r1 = 0;
+    for (uint32_t k = 0; k < n; k += 4) {
+        const float4 e0 = L[k];
+        const float4 e1 = (k + 1 < n) ? L[k + 1] : far;
+        const float4 e2 = (k + 2 < n) ? L[k + 2] : far;
+        const float4 e3 = (k + 3 < n) ? L[k + 3] : far;
+        float dx, dy, dz, d;
+        dx = e0.x - x; dy = e0.y - y; dz = e0.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e0.w); } else m2 = fminf(m2, d);
+        dx = e1.x - x; dy = e1.y - y; dz = e1.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e1.w); } else m2 = fminf(m2, d);
+        dx = e2.x - x; dy = e2.y - y; dz = e2.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e2.w); } else m2 = fminf(m2, d);
+        dx = e3.x - x; dy = e3.y - y; dz = e3.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e3.w); } else m2 = fminf(m2, d);
+    }
+    const float thr = fmaf(m1, 3e-6f, m1) + V.band_abs;
+    {
+        const GridPoint gp = pts[r1];
+        best = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
+        bidx = gp.orig;
+    }
+    n_gather = 1;
+    if (m2 <= thr) {                                     // more than one entry inside the FP32 error band: decide in FP64
+        for (uint32_t k = 0; k < n; ++k) {
+            const float4 en = L[k];
+            const float dx = en.x - x, dy = en.y - y, dz = en.z - z;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const int r = __float_as_int(en.w);
+            if (d <= thr && r != r1) {
+                const GridPoint gp = pts[r];
+                const double dd = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
+                if (dd < best || (dd == best && gp.orig < bidx)) { best = dd; bidx = gp.orig; }
+                ++n_gather;
+            }
+        }
+    }
+}
+
+}  // namespace pcreg

@@ -116,3 +116,67 @@ def test_voxel_map_icp_equals_brute_force_icp(pcreg):
         assert np.array_equal(a[k], b[k]), k
     assert prof["voxel_map"] == 1 and prof["certified_queries"] > 0.95 * prof["nn_queries"], prof
     m.destroy()
+
+
+@pytest.mark.parametrize("mode", ["plain-reject", "knn", "knn-reject", "weighted"])
+def test_fused_kernel_equals_per_pass_kernels_and_brute_force(pcreg, monkeypatch, mode):
+    """icp_fused.cu runs all passes of a hypothesis in one block; it must return the bits of the per-pass kernels
+    (PCREG_FUSED=0: k_nn_vox + k_icp_update) and of the brute-force path, for every selection mode."""
+    model = synth.make_model(80_000, 191)
+    src, T_gt, c = synth.make_source(model, 1500, 0.3, 192)
+    g = synth.rng(7)
+    src = np.vstack([src, src[:200] + g.normal(0, 2.5, (200, 3))])            # some gross outliers
+    T0 = synth.pose_grid(T_gt, c, 3, (2, 2, 2), 12.0, 2.0, 19)[:21]
+    kw = {"plain-reject": dict(mode=pcreg.ICP_PLAIN, thDist2=4.0), "knn": dict(mode=pcreg.ICP_KNN),
+          "knn-reject": dict(mode=pcreg.ICP_KNN, thDist2=9.0, k_frac=0.7),
+          "weighted": dict(mode=pcreg.ICP_WEIGHTED, R_w=3.5, w_src=g.uniform(0.5, 1.0, src.shape[0]))}[mode]
+    m = pcreg.Model(model, grid=True)
+    pcreg.set_profiling(True)
+    a = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_GRID, return_idx=True, return_hist=True, **kw)
+    prof = pcreg.last_profile()
+    pcreg.set_profiling(False)
+    assert prof["fused"] == 1 and prof["voxel_map"] == 1, prof
+    monkeypatch.setenv("PCREG_FUSED", "0")
+    b = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_GRID, return_idx=True, return_hist=True, **kw)
+    monkeypatch.delenv("PCREG_FUSED")
+    r = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True, **kw)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k], b[k], equal_nan=True) if a[k].dtype.kind == "f" else np.array_equal(a[k], b[k]), ("fused vs per-pass", k)
+        assert np.array_equal(a[k], r[k], equal_nan=True) if a[k].dtype.kind == "f" else np.array_equal(a[k], r[k]), ("fused vs brute", k)
+    assert a["best"] == b["best"] == r["best"]
+    m.destroy()
+
+
+def test_fused_kernel_walks_queries_without_a_list(pcreg, monkeypatch):
+    """Dropped lists (tiny cap) and queries outside the unpadded box: the fused kernel walks the pyramid for them in place."""
+    model = synth.make_model(60_000, 23)
+    src, T_gt, c = synth.make_source(model, 1200, 0.3, 24)
+    T0 = synth.pose_grid(T_gt, c, 2, (2, 2, 2), 10.0, 3.0, 3)
+    monkeypatch.setenv("PCREG_VOX_CAP", "8")
+    m = pcreg.Model(model, grid=True, voxel_map=1, voxel_margin=-1.0)
+    monkeypatch.delenv("PCREG_VOX_CAP")
+    pcreg.set_profiling(True)
+    a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=10, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    prof = pcreg.last_profile()
+    pcreg.set_profiling(False)
+    assert prof["fused"] == 1 and prof["walked_queries"] > 0, prof
+    r = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=10, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k], r[k]), k
+    m.destroy()
+
+
+def test_fused_kernel_frozen_and_short_sources(pcreg):
+    """Fewer than 3 usable correspondences freezes the pose (status 1); tiny sources (ns < block size, ns = 1)."""
+    model = synth.make_model(20_000, 300)
+    for ns in (1, 2, 37, 600):
+        src, T_gt, c = synth.make_source(model, max(ns, 4), 0.3, 301)
+        src = src[:ns]
+        T0 = synth.pose_grid(T_gt, c, 2, (2, 1, 1), 5.0, 1.0, 3)
+        m = pcreg.Model(model, grid=True)
+        for kw in (dict(mode=pcreg.ICP_PLAIN, thDist2=1e-12), dict(mode=pcreg.ICP_KNN), dict(mode=pcreg.ICP_PLAIN)):
+            a = pcreg.icp_batch(m, src, T0, iters=5, nn=pcreg.NN_GRID, return_idx=True, return_hist=True, **kw)
+            r = pcreg.icp_batch(m, src, T0, iters=5, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True, **kw)
+            for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+                assert np.array_equal(a[k], r[k], equal_nan=True) if a[k].dtype.kind == "f" else np.array_equal(a[k], r[k]), (ns, kw, k)
+        m.destroy()
