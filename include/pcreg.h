@@ -276,7 +276,8 @@ int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
  *   out[26] = 1 when the grid NN ran on the model's Voronoi voxel map: then out[10] = queries answered by the voxel list
  *   scan, out[13] = list entries read, out[14] = points gathered for the FP64 decision, out[17] / out[20] = ms / launches
  *   of the list-scan kernel, and out[11], out[15], out[16], out[9], out[19] describe the pyramid walk of the rest.
- *   out[27] = 1 when the whole ICP ran as the fused per-hypothesis kernel (one launch; out[1] = out[17] = its ms).
+ *   out[27] = 1 when the whole ICP ran as the fused per-hypothesis kernel (one launch; out[1] = out[17] = its ms);
+ *   out[28..31] = share of a block's cycles in its four phases (NN, trim selection, 17 sums + reduction, pose update).
  * Collected only when enabled: the counters add atomics to the kernels, so timed runs keep it off.
  * enabled = 1: event times + work counters; 2: event times only (kernel times undisturbed by the counter atomics). */
 int  pcreg_set_profiling(int enabled);

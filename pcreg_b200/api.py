@@ -508,7 +508,7 @@ def last_profile() -> dict:
                 list_entries_read=v[13], list_points_gathered=v[14],
                 rowscan_points=v[7], rowscan_rows=v[8], walk_points=v[15], walk_leaves=v[16],
                 list_ms=v[17], rowscan_ms=v[18], walk_ms=v[19], list_launches=v[20], rowscan_launches=v[21], walk_launches=v[22],
-                match_score_ms=v[24], match_terms=v[25], voxel_map=v[26], fused=v[27])
+                match_score_ms=v[24], match_terms=v[25], voxel_map=v[26], fused=v[27], fused_phase_share=dict(nn=v[28], select=v[29], sums=v[30], svd=v[31]))
 
 
 def launch_count() -> int:

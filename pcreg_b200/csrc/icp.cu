@@ -506,6 +506,9 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
             c.profile[13] = (double)hcnt[6]; c.profile[14] = (double)hcnt[7];
             c.profile[17] = ms; c.profile[20] = 1;
             c.profile[26] = 1.0; c.profile[27] = 1.0;
+            // share of a block's cycles spent in each phase (clock64 of thread 0, summed over the blocks)
+            const double tot = (double)hcnt[11] + (double)hcnt[12] + (double)hcnt[13] + (double)hcnt[14];
+            for (int k = 0; k < 4; ++k) c.profile[28 + k] = tot > 0.0 ? (double)hcnt[11 + k] / tot : 0.0;
         }
         return;
     }

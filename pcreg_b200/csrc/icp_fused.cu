@@ -4,12 +4,12 @@
 //
 // Why.  With the Voronoi voxel map (nn_vox.cu) an NN pass costs ~0.6 ms for 20 M queries; the per-pass kernels then spend as
 // much again writing correspondences / residuals / trim keys to HBM and reading them back, and a small batch (strong scaling:
-// 512 hypotheses per GPU) is bound by the 60-odd launches.  Here the correspondences and the trim keys of a hypothesis live in
+// a few hundred hypotheses per GPU) is bound by the 60-odd launches.  Here the correspondences and the trim keys of a hypothesis live in
 // SHARED memory (4 + 8 bytes per source point), the pose in shared memory, and nothing but the voxel lists, the source cloud
 // and the gathered model points is read from global memory; there is one launch per batch and no host synchronisation.
 //
 // Same arithmetic as the per-pass path (pcreg_icp.cuh, pcreg_vox.cuh, pcreg_select.cuh are shared; thread t sums the
-// correspondences t, t + 512, ... in both), so poses, RMSE history and correspondences are bit-identical to it and to the
+// correspondences t, t + UPD_THREADS, ... in both), so poses, RMSE history and correspondences are bit-identical to it and to the
 // brute-force path (tests/test_gpu_icp.py).  Composition as in icp.cu: quickTF.m:5-7, ransac.m:49, AlignPoints_KNN.m:20-26,
 // AlignPoints_weighted.m:16-18, estimateTransform.m:41-71.
 // A query whose voxel has no list (or that lies outside the padded box) is walked through the occupancy pyramid by its own
@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
     const bool knn = a.mode == PCREG_ICP_KNN;
     const double px = a.pivot[0], py = a.pivot[1], pz = a.pivot[2];
     unsigned long long c_read = 0, c_gather = 0, c_walk = 0;
+    long long t_nn = 0, t_sel = 0, t_sum = 0, t_svd = 0, t_mark = 0;       // phase clocks of thread 0 (profiling only)
+    const bool timing = a.counters != nullptr && tid == 0;
 
     if (tid < 16) Ts[tid] = a.T[h * 16 + tid];
     if (tid == 0) s_frozen = a.frozen[h];
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
         // ---- exact nearest neighbours of the hypothesis' ns queries (two per trip: their header / entry loads overlap) ----
         long long nkept = 0;
         unsigned long long kmin = ~0ull, kmax = 0ull;
+        if (timing) t_mark = clock64();
         for (int i0 = tid; i0 < ns; i0 += 2 * UPD_THREADS) {
             const int i1 = i0 + UPD_THREADS;
             const bool has1 = i1 < ns;
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
             }
         }
         __syncthreads();
+        if (timing) { const long long t = clock64(); t_nn += t - t_mark; t_mark = t; }
         // ---- trim: the round(k_frac * kept) smallest residuals, stable tie rule (AlignPoints_KNN.m:20-26) ----
         unsigned long long vK = 0ull;
         bool all_eq = false;
@@ -137,7 +141,8 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
             if (K > nkept) K = nkept;
             block_hist_select(keys_s, ns, K, kmin, kmax, hsel, vK, all_eq, a.tie_order);
         }
-        // ---- weights + the 17 sums (thread t: correspondences t, t + 512, ... in this order, as k_icp_update) ----
+        if (timing) { const long long t = clock64(); t_sel += t - t_mark; t_mark = t; }
+        // ---- weights + the 17 sums (thread t: correspondences t, t + UPD_THREADS, ... in this order, as k_icp_update) ----
         double s[KABSCH_NSUMS];
 #pragma unroll
         for (int k = 0; k < KABSCH_NSUMS; ++k) s[k] = 0.0;
@@ -159,6 +164,7 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
         }
         block_sum<KABSCH_NSUMS>(s, red);
         n_used = block_sum_ll(n_used, redll);
+        if (timing) { const long long t = clock64(); t_sum += t - t_mark; t_mark = t; }
         if (tid == 0) {
             const double sw = s[0];
             const double rmse = (sw > 0.0) ? sqrt(s[16] / sw) : nan("");
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
                 if (!fused_pose_update(s, n_used, a.pivot, a.reflection_fix != 0, Ts)) s_frozen = 1;
             }
         }
+        if (timing) { const long long t = clock64(); t_svd += t - t_mark; t_mark = t; }
         __syncthreads();
     }
     if (tid < 16) a.T[h * 16 + tid] = Ts[tid];
@@ -182,6 +189,10 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
             c_read += __shfl_xor_sync(0xffffffffu, c_read, o);
             c_gather += __shfl_xor_sync(0xffffffffu, c_gather, o);
             c_walk += __shfl_xor_sync(0xffffffffu, c_walk, o);
+        }
+        if (tid == 0) {
+            atomicAdd(&a.counters[11], (unsigned long long)t_nn); atomicAdd(&a.counters[12], (unsigned long long)t_sel);
+            atomicAdd(&a.counters[13], (unsigned long long)t_sum); atomicAdd(&a.counters[14], (unsigned long long)t_svd);
         }
         if ((tid & 31) == 0) {
             if (c_read) atomicAdd(&a.counters[6], c_read);

@@ -16,8 +16,8 @@ namespace pcreg {
 #ifdef UPD_THREADS_OVERRIDE
 constexpr int UPD_THREADS = UPD_THREADS_OVERRIDE;
 #else
-constexpr int UPD_THREADS = 512;
-#endif
+constexpr int UPD_THREADS = 384;       // 80 registers x 2 blocks per SM for the fused kernel (measured: 44 ms per C3 step; 512 threads at 64
+#endif                                 // registers spill: 48-53 ms; 512 x 1 block at 128 registers: 45 ms; 256 x 3: 51 ms)
 #ifndef FUSED_MIN_BLOCKS
 #define FUSED_MIN_BLOCKS 2
 #endif
