@@ -36,10 +36,17 @@ extern "C" {
 typedef struct pcreg_model pcreg_model;   /* opaque, GPU-resident model cloud */
 
 /* ---- library lifetime ------------------------------------------------------------------- */
-/* One process drives ONE GPU (one process per GPU; multi-GPU = one rank per GPU sharding the
- * hypothesis batch, see pcreg_b200/sharded.py).  devices[0] is the CUDA ordinal; ndev must be 1.
- * devices == NULL selects ordinal 0. */
+/* devices[0..ndev) are CUDA ordinals (devices == NULL or ndev == 0: ordinal 0).  With ndev > 1 the library drives all of
+ * them from this one process -- the replacement of the reference's parfor over windows / trials
+ * (slideMatchingWindow_v2.m:178, completeExperiment.m:265): pcreg_model_create replicates the model on every device,
+ * pcreg_icp_batch shards its hypotheses and pcreg_ransac_batch its windows contiguously over the devices (one host thread
+ * and stream set per device, no communication during the iterations), every device copies its result records straight
+ * into its slice of the caller's arrays, and the winner is the first-index arg-min over all of them.  Results are
+ * bit-identical for any ndev.  The other entry points run on devices[0].  Calling pcreg_init again re-initialises
+ * (model handles of the previous device set become invalid).  One process per GPU over torch.distributed
+ * (pcreg_b200/sharded.py) remains possible: each rank then calls pcreg_init with its own ordinal. */
 int  pcreg_init(const int* devices, int ndev);
+int  pcreg_device_count(void);              /* number of devices selected by the last pcreg_init (0 before) */
 int  pcreg_shutdown(void);
 const char* pcreg_last_error(void);
 /* Number of kernels this library launched since pcreg_init (bench.py's gpu_launches claim). */

@@ -55,6 +55,7 @@ class IcpOpts(C.Structure):
 SIGNATURES = {
     "pcreg_init": (C.c_int, [c_i32p, C.c_int]),
     "pcreg_shutdown": (C.c_int, []),
+    "pcreg_device_count": (C.c_int, []),
     "pcreg_last_error": (C.c_char_p, []),
     "pcreg_launch_count": (C.c_int64, []),
     "pcreg_abi_version": (C.c_int, []),
@@ -126,18 +127,28 @@ def check(rc: int, what: str) -> int:
     return rc
 
 
-def init(device: int | None = None):
-    """pcreg_init on `device` (default: LOCAL_RANK or 0).  Raises without a usable B200."""
+def init(device=None):
+    """pcreg_init on `device` -- an ordinal (default: LOCAL_RANK or 0) or a sequence of ordinals: with several devices the
+    model is replicated on each and pcreg_icp_batch / pcreg_ransac_batch shard their hypotheses / windows over them inside
+    the library (one host thread per device).  Raises without a usable B200."""
     global _initialised_device
     lib = load()
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
-    if _initialised_device == device:
+    devs = tuple(int(d) for d in device) if hasattr(device, "__len__") else (int(device),)
+    if _initialised_device == devs:
         return lib
-    dev = (C.c_int32 * 1)(device)
-    check(lib.pcreg_init(dev, 1), "pcreg_init")
-    _initialised_device = device
+    arr = (C.c_int32 * len(devs))(*devs)
+    check(lib.pcreg_init(arr, len(devs)), "pcreg_init")
+    _initialised_device = devs
     return lib
+
+
+def shutdown():
+    global _initialised_device
+    if _lib is not None:
+        _lib.pcreg_shutdown()
+    _initialised_device = None
 
 
 def lib():

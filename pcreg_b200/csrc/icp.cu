@@ -17,6 +17,7 @@
 #include <time.h>
 #include <algorithm>
 #include <vector>
+#include <thread>
 
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
@@ -672,6 +673,30 @@ int pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns, c
     PCREG_API_END
 }
 
+// One device's share [h0, h0 + hn) of a host-buffer batch, on the calling thread's slot.  Output pointers are the caller's
+// arrays (whole batch); every copy lands in its own contiguous slice, which is the "all-gather" of SURVEY.md section 8e.
+static void icp_batch_host_slice(const pcreg_model* m, const std::vector<double>& hs, int64_t ns, const double* w_src,
+                                 const double* T0_16, int64_t h0, int64_t hn, const pcreg_icp_opts& o, double* T16, double* rmse,
+                                 int32_t* n_used, int32_t* status, int32_t* idx, double* rmse_hist) {
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    cudaStream_t st = 0;
+    DevBuf<double> d_src((size_t)ns * 3), d_w(w_src ? (size_t)ns : 0), d_T0((size_t)hn * 16), d_T((size_t)hn * 16);
+    DevBuf<double> d_rmse((size_t)hn), d_hist(rmse_hist ? (size_t)hn * (o.iters + 1) : 0);
+    DevBuf<int32_t> d_nu((size_t)hn), d_st((size_t)hn), d_idx(idx ? (size_t)hn * ns : 0);
+    PCREG_CUDA(cudaMemcpyAsync(d_src.p, hs.data(), d_src.bytes(), cudaMemcpyHostToDevice, st));
+    if (w_src) PCREG_CUDA(cudaMemcpyAsync(d_w.p, w_src, d_w.bytes(), cudaMemcpyHostToDevice, st));
+    PCREG_CUDA(cudaMemcpyAsync(d_T0.p, T0_16 + h0 * 16, d_T0.bytes(), cudaMemcpyHostToDevice, st));
+    icp_run(m, d_src.p, ns, w_src ? d_w.p : nullptr, d_T0.p, hn, o, d_T.p, d_rmse.p, d_nu.p, d_st.p,
+            idx ? d_idx.p : nullptr, rmse_hist ? d_hist.p : nullptr, nullptr, st);
+    PCREG_CUDA(cudaMemcpyAsync(T16 + h0 * 16, d_T.p, d_T.bytes(), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaMemcpyAsync(rmse + h0, d_rmse.p, d_rmse.bytes(), cudaMemcpyDeviceToHost, st));
+    if (n_used) PCREG_CUDA(cudaMemcpyAsync(n_used + h0, d_nu.p, d_nu.bytes(), cudaMemcpyDeviceToHost, st));
+    if (status) PCREG_CUDA(cudaMemcpyAsync(status + h0, d_st.p, d_st.bytes(), cudaMemcpyDeviceToHost, st));
+    if (idx) PCREG_CUDA(cudaMemcpyAsync(idx + h0 * ns, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
+    if (rmse_hist) PCREG_CUDA(cudaMemcpyAsync(rmse_hist + h0 * (o.iters + 1), d_hist.p, d_hist.bytes(), cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));
+}
+
 int pcreg_icp_batch(const pcreg_model* m, const void* src, int is_double, int64_t ns, int64_t ld, const double* w_src,
                     const double* T0_16, int64_t nhyp, const pcreg_icp_opts* opts, double* T16, double* rmse,
                     int32_t* n_used, int32_t* status, int32_t* idx, double* rmse_hist, int64_t* best) {
@@ -679,26 +704,32 @@ int pcreg_icp_batch(const pcreg_model* m, const void* src, int is_double, int64_
     require_init();
     PCREG_REQUIRE(m && src && T0_16 && T16 && opts, "pcreg_icp_batch: null pointer");
     PCREG_REQUIRE(ns >= 1 && ld >= ns && nhyp >= 1, "pcreg_icp_batch: bad sizes");
-    PCREG_CUDA(cudaSetDevice(ctx().device));
-    cudaStream_t st = 0;
-    std::vector<double> hs = to_double_cm(src, is_double, ns, ld);
-    DevBuf<double> d_src((size_t)ns * 3), d_w(w_src ? (size_t)ns : 0), d_T0((size_t)nhyp * 16), d_T((size_t)nhyp * 16);
-    DevBuf<double> d_rmse((size_t)nhyp), d_hist(rmse_hist ? (size_t)nhyp * (opts->iters + 1) : 0);
-    DevBuf<int32_t> d_nu((size_t)nhyp), d_st((size_t)nhyp), d_idx(idx ? (size_t)nhyp * ns : 0);
-    DevBuf<int64_t> d_best(1);
-    PCREG_CUDA(cudaMemcpyAsync(d_src.p, hs.data(), d_src.bytes(), cudaMemcpyHostToDevice, st));
-    if (w_src) PCREG_CUDA(cudaMemcpyAsync(d_w.p, w_src, d_w.bytes(), cudaMemcpyHostToDevice, st));
-    PCREG_CUDA(cudaMemcpyAsync(d_T0.p, T0_16, d_T0.bytes(), cudaMemcpyHostToDevice, st));
-    icp_run(m, d_src.p, ns, w_src ? d_w.p : nullptr, d_T0.p, nhyp, *opts, d_T.p, d_rmse.p, d_nu.p, d_st.p,
-            idx ? d_idx.p : nullptr, rmse_hist ? d_hist.p : nullptr, d_best.p, st);
-    PCREG_CUDA(cudaMemcpyAsync(T16, d_T.p, d_T.bytes(), cudaMemcpyDeviceToHost, st));
-    if (rmse) PCREG_CUDA(cudaMemcpyAsync(rmse, d_rmse.p, d_rmse.bytes(), cudaMemcpyDeviceToHost, st));
-    if (n_used) PCREG_CUDA(cudaMemcpyAsync(n_used, d_nu.p, d_nu.bytes(), cudaMemcpyDeviceToHost, st));
-    if (status) PCREG_CUDA(cudaMemcpyAsync(status, d_st.p, d_st.bytes(), cudaMemcpyDeviceToHost, st));
-    if (idx) PCREG_CUDA(cudaMemcpyAsync(idx, d_idx.p, d_idx.bytes(), cudaMemcpyDeviceToHost, st));
-    if (rmse_hist) PCREG_CUDA(cudaMemcpyAsync(rmse_hist, d_hist.p, d_hist.bytes(), cudaMemcpyDeviceToHost, st));
-    if (best) PCREG_CUDA(cudaMemcpyAsync(best, d_best.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    PCREG_CUDA(cudaStreamSynchronize(st));
+    const std::vector<double> hs = to_double_cm(src, is_double, ns, ld);
+    std::vector<double> rmse_tmp(rmse ? 0 : (size_t)nhyp);
+    double* rm = rmse ? rmse : rmse_tmp.data();
+    // Hypotheses are independent (the reference runs them under parfor: slideMatchingWindow_v2.m:178, completeExperiment.m:265):
+    // contiguous shares, one host thread + stream per selected device, the model replicated by pcreg_model_create; no
+    // communication until the result records land in the caller's arrays.
+    const int nd = (int)std::min<int64_t>(num_slots(), std::min<int64_t>(nhyp, (int64_t)m->replicas.size() + 1));
+    const int64_t per = (nhyp + nd - 1) / nd;
+    std::vector<int> rc((size_t)nd, PCREG_OK);
+    std::vector<std::thread> workers;
+    for (int k = 1; k < nd; ++k) {
+        const int64_t h0 = k * per, hn = std::min(per, nhyp - h0);
+        if (hn <= 0) continue;
+        workers.emplace_back([&, k, h0, hn]() {
+            rc[k] = guarded([&]() { use_slot(k); icp_batch_host_slice(m->on_slot(k), hs, ns, w_src, T0_16, h0, hn, *opts, T16, rm, n_used, status, idx, rmse_hist); });
+        });
+    }
+    rc[0] = guarded([&]() { use_slot(0); icp_batch_host_slice(m, hs, ns, w_src, T0_16, 0, std::min(per, nhyp), *opts, T16, rm, n_used, status, idx, rmse_hist); });
+    for (auto& w : workers) w.join();
+    use_slot(0);
+    for (int k = 0; k < nd; ++k) if (rc[k] != PCREG_OK) return rc[k];
+    if (best) {                                           // first-index arg-min, NaN never wins (ransac.m:69-73 tie rule mirrored)
+        int64_t bi = -1;
+        for (int64_t h = 0; h < nhyp; ++h) if (rm[h] == rm[h] && (bi < 0 || rm[h] < rm[bi])) bi = h;
+        *best = bi;
+    }
     return PCREG_OK;
     PCREG_API_END
 }

@@ -5,6 +5,7 @@
 #include <float.h>
 #include <algorithm>
 #include <vector>
+#include <thread>
 
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
@@ -543,20 +544,14 @@ int pcreg_ransac_run(const double* p1, const double* p2, int64_t P, int64_t ld, 
     PCREG_API_END
 }
 
-int pcreg_ransac_batch(const double* p1, const double* p2, int64_t ld, const int64_t* offsets, int64_t nwin, int64_t iter_num,
-                       const int32_t* triplets, const uint64_t* seeds, const pcreg_ransac_opts* opts, double* T16,
-                       int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ, int64_t* max_inl, int64_t* best_hyp, int32_t* status) {
-    PCREG_API_BEGIN
-    require_init();
-    PCREG_REQUIRE(p1 && p2 && offsets && opts && T16 && inl_idx && n_inl && n_succ && max_inl && best_hyp && status,
-                  "pcreg_ransac_batch: null pointer");
-    PCREG_REQUIRE(triplets || seeds, "pcreg_ransac_batch: need triplets or seeds");
-    PCREG_REQUIRE(nwin >= 1 && iter_num >= 1, "pcreg_ransac_batch: need nwin >= 1 and iter_num >= 1");
+}  // extern "C" (the slice helper below is internal)
+
+// The windows [0, nwin) described by `offsets` (offsets[0] = 0) on the calling thread's device slot.
+static void ransac_batch_slice(const double* p1, const double* p2, int64_t ld, const int64_t* offsets, int64_t nwin, int64_t iter_num,
+                               const int32_t* triplets, const uint64_t* seeds, const pcreg_ransac_opts* opts, double* T16,
+                               int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ, int64_t* max_inl, int64_t* best_hyp, int32_t* status) {
     const int64_t ntotal = offsets[nwin];
-    PCREG_REQUIRE(offsets[0] == 0 && ntotal >= 0 && ld >= ntotal, "pcreg_ransac_batch: bad offsets / ld");
-    for (int64_t w = 0; w < nwin; ++w) PCREG_REQUIRE(offsets[w + 1] >= offsets[w], "pcreg_ransac_batch: offsets must be non-decreasing");
     const int64_t nhyp = nwin * iter_num;
-    PCREG_REQUIRE(nhyp < ((int64_t)1 << 26), "pcreg_ransac_batch: more than 2^26 hypotheses in one call");
     PCREG_CUDA(cudaSetDevice(ctx().device));
     cudaStream_t st = 0;
     const size_t nel = (size_t)std::max<int64_t>(ntotal, 1);
@@ -607,6 +602,47 @@ int pcreg_ransac_batch(const double* p1, const double* p2, int64_t ld, const int
                 if (hf[(size_t)i]) inl_idx[offsets[w] + ni++] = (int32_t)(i - offsets[w]);
         n_inl[w] = ni;
     }
+}
+
+extern "C" {
+
+int pcreg_ransac_batch(const double* p1, const double* p2, int64_t ld, const int64_t* offsets, int64_t nwin, int64_t iter_num,
+                       const int32_t* triplets, const uint64_t* seeds, const pcreg_ransac_opts* opts, double* T16,
+                       int32_t* inl_idx, int64_t* n_inl, int64_t* n_succ, int64_t* max_inl, int64_t* best_hyp, int32_t* status) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(p1 && p2 && offsets && opts && T16 && inl_idx && n_inl && n_succ && max_inl && best_hyp && status,
+                  "pcreg_ransac_batch: null pointer");
+    PCREG_REQUIRE(triplets || seeds, "pcreg_ransac_batch: need triplets or seeds");
+    PCREG_REQUIRE(nwin >= 1 && iter_num >= 1, "pcreg_ransac_batch: need nwin >= 1 and iter_num >= 1");
+    const int64_t ntotal = offsets[nwin];
+    PCREG_REQUIRE(offsets[0] == 0 && ntotal >= 0 && ld >= ntotal, "pcreg_ransac_batch: bad offsets / ld");
+    for (int64_t w = 0; w < nwin; ++w) PCREG_REQUIRE(offsets[w + 1] >= offsets[w], "pcreg_ransac_batch: offsets must be non-decreasing");
+    const int64_t nhyp = nwin * iter_num;
+    PCREG_REQUIRE(nhyp < ((int64_t)1 << 26), "pcreg_ransac_batch: more than 2^26 hypotheses in one call");
+    // Windows are independent (the reference runs one ransac per window under parfor, slideMatchingWindow_v2.m:178): contiguous
+    // shares of windows, one host thread per selected device; each window's result equals the single-window call, so the
+    // split changes no bit.
+    const int nd = (int)std::min<int64_t>(num_slots(), nwin);
+    const int64_t per = (nwin + nd - 1) / nd;
+    std::vector<int> rc((size_t)nd, PCREG_OK);
+    std::vector<std::thread> workers;
+    auto run = [&](int k) {
+        const int64_t w0 = k * per, wn = std::min(per, nwin - w0);
+        if (wn <= 0) return;
+        std::vector<int64_t> off((size_t)wn + 1);
+        for (int64_t w = 0; w <= wn; ++w) off[(size_t)w] = offsets[w0 + w] - offsets[w0];
+        const int64_t r0 = offsets[w0];
+        use_slot(k);
+        ransac_batch_slice(p1 + r0, p2 + r0, ld, off.data(), wn, iter_num, triplets ? triplets + w0 * iter_num * 3 : nullptr,
+                           seeds ? seeds + w0 : nullptr, opts, T16 + w0 * 16, inl_idx + r0, n_inl + w0, n_succ + w0, max_inl + w0,
+                           best_hyp + w0, status + w0);
+    };
+    for (int k = 1; k < nd; ++k) workers.emplace_back([&, k]() { rc[k] = guarded([&]() { run(k); }); });
+    rc[0] = guarded([&]() { run(0); });
+    for (auto& w : workers) w.join();
+    use_slot(0);
+    for (int k = 0; k < nd; ++k) if (rc[k] != PCREG_OK) return rc[k];
     return PCREG_OK;
     PCREG_API_END
 }

@@ -7,9 +7,12 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <functional>
 #include <vector>
 #include <algorithm>
 
@@ -21,7 +24,9 @@ namespace pcreg {
 static thread_local char g_err[1024] = "";
 static char g_err_global[1024] = "";
 static std::atomic<long long> g_launches{0};
-static Context g_ctx;
+static Context g_ctxs[PCREG_MAX_DEVICES];
+static int g_nslots = 0;
+static thread_local int tl_slot = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -32,22 +37,38 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-// ---- caching device allocator ----
-struct PoolBlock { void* p; size_t bytes; bool used; };
-static std::vector<PoolBlock> g_pool;
+// ---- caching device allocator (one pool per device; blocks are found by pointer, so a buffer may be released from
+// any host thread) ----
 static std::mutex g_pool_mu;
 static constexpr size_t POOL_KEEP_BYTES = (size_t)24 << 30;
-
+static void pool_trim_locked(Context& c, size_t keep_bytes) {
+    size_t free_bytes = 0;
+    for (auto& b : c.pool) if (!b.used) free_bytes += b.bytes;
+    if (free_bytes <= keep_bytes) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c.device);
+    for (size_t i = 0; i < c.pool.size() && free_bytes > keep_bytes;) {
+        if (!c.pool[i].used) {
+            cudaFree(c.pool[i].p);
+            free_bytes -= c.pool[i].bytes;
+            c.pool[i] = c.pool.back();
+            c.pool.pop_back();
+        } else ++i;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+}
 void* pool_alloc(size_t bytes) {
     bytes = (bytes + 511) & ~(size_t)511;
+    Context& c = ctx();
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         int best = -1;
-        for (int i = 0; i < (int)g_pool.size(); ++i) {
-            const PoolBlock& b = g_pool[i];
-            if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (best < 0 || b.bytes < g_pool[best].bytes)) best = i;
+        for (int i = 0; i < (int)c.pool.size(); ++i) {
+            const PoolBlock& b = c.pool[i];
+            if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (best < 0 || b.bytes < c.pool[best].bytes)) best = i;
         }
-        if (best >= 0) { g_pool[best].used = true; return g_pool[best].p; }
+        if (best >= 0) { c.pool[best].used = true; return c.pool[best].p; }
     }
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, bytes);
@@ -58,33 +79,29 @@ void* pool_alloc(size_t bytes) {
         if (e != cudaSuccess) throw CudaFail{e, "cudaMalloc", __FILE__, __LINE__};
     }
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    g_pool.push_back(PoolBlock{q, bytes, true});
+    c.pool.push_back(PoolBlock{q, bytes, true});
     return q;
 }
 void pool_free(void* p) {
     if (!p) return;
-    size_t free_bytes = 0;
-    {
-        std::lock_guard<std::mutex> lk(g_pool_mu);
-        for (auto& b : g_pool) {
-            if (b.p == p) b.used = false;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (int k = 0; k < std::max(g_nslots, 1); ++k) {
+        Context& c = g_ctxs[k];
+        bool mine = false;
+        size_t free_bytes = 0;
+        for (auto& b : c.pool) {
+            if (b.p == p) { b.used = false; mine = true; }
             if (!b.used) free_bytes += b.bytes;
         }
+        if (mine) {
+            if (free_bytes > POOL_KEEP_BYTES) pool_trim_locked(c, POOL_KEEP_BYTES / 2);
+            return;
+        }
     }
-    if (free_bytes > POOL_KEEP_BYTES) pool_trim(POOL_KEEP_BYTES / 2);
 }
 void pool_trim(size_t keep_bytes) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    size_t free_bytes = 0;
-    for (auto& b : g_pool) if (!b.used) free_bytes += b.bytes;
-    for (size_t i = 0; i < g_pool.size() && free_bytes > keep_bytes;) {
-        if (!g_pool[i].used) {
-            cudaFree(g_pool[i].p);
-            free_bytes -= g_pool[i].bytes;
-            g_pool[i] = g_pool.back();
-            g_pool.pop_back();
-        } else ++i;
-    }
+    pool_trim_locked(ctx(), keep_bytes);
 }
 cudaEvent_t pooled_event(size_t i) {
     Context& c = ctx();
@@ -104,12 +121,19 @@ cudaStream_t lane_stream(int i) {
     }
     return c.streams[i];
 }
-Context& ctx() { return g_ctx; }
+Context& ctx() { return g_ctxs[tl_slot]; }
+int num_slots() { return g_nslots; }
+int current_slot() { return tl_slot; }
+void use_slot(int slot) {
+    if (slot < 0 || slot >= std::max(g_nslots, 1)) throw ArgError{"internal: bad device slot"};
+    tl_slot = slot;
+    if (g_ctxs[slot].initialised) PCREG_CUDA(cudaSetDevice(g_ctxs[slot].device));
+}
 
 constexpr size_t PINNED_BYTES = (size_t)16 << 20;
 void h2d_columns(double* d_dst, int64_t ld_dst, const double* h_src, int64_t ld_src, int64_t rows, int64_t ncols, cudaStream_t st) {
     if (rows <= 0 || ncols <= 0) return;
-    Context& c = g_ctx;
+    Context& c = ctx();
     for (int b = 0; b < 2; ++b) {
         if (!c.pinned[b]) {
             PCREG_CUDA(cudaHostAlloc(&c.pinned[b], PINNED_BYTES, cudaHostAllocDefault));
@@ -139,7 +163,7 @@ void h2d_columns(double* d_dst, int64_t ld_dst, const double* h_src, int64_t ld_
     for (int k = 0; k < 2; ++k) if (used[k]) PCREG_CUDA(cudaEventSynchronize(c.pinned_ev[k]));
 }
 void require_init() {
-    if (!g_ctx.initialised) throw ArgError{"pcreg_init has not been called (or failed): no CUDA device, and there is no CPU fallback"};
+    if (!ctx().initialised) throw ArgError{"pcreg_init has not been called (or failed): no CUDA device, and there is no CPU fallback"};
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,8 +413,9 @@ int64_t pcreg_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int pcreg_init(const int* devices, int ndev) {
     PCREG_API_BEGIN
-    PCREG_REQUIRE(ndev <= 1, "pcreg_init: one process drives one GPU (ndev must be 1); shard hypotheses across ranks");
-    const int dev = (devices && ndev == 1) ? devices[0] : 0;
+    PCREG_REQUIRE(ndev >= 0 && ndev <= PCREG_MAX_DEVICES, "pcreg_init: ndev out of range");
+    PCREG_REQUIRE(ndev <= 1 || devices, "pcreg_init: devices is null");
+    if (g_nslots > 0) pcreg_shutdown();                 // re-initialisation: drop the previous device set
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) {
@@ -399,87 +424,86 @@ int pcreg_init(const int* devices, int ndev) {
         cudaGetLastError();
         return PCREG_ERR_CUDA;
     }
-    PCREG_REQUIRE(dev >= 0 && dev < count, "pcreg_init: device ordinal out of range");
-    PCREG_CUDA(cudaSetDevice(dev));
-    cudaDeviceProp p;
-    PCREG_CUDA(cudaGetDeviceProperties(&p, dev));
-    if (p.major < 10) {
-        set_error("pcreg_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, p.major, p.minor);
-        return PCREG_ERR_CUDA;
+    const int n = std::max(ndev, 1);
+    for (int k = 0; k < n; ++k) {
+        const int dev = (devices && ndev >= 1) ? devices[k] : 0;
+        PCREG_REQUIRE(dev >= 0 && dev < count, "pcreg_init: device ordinal out of range");
+        // (PCREG_ALLOW_DUP_DEVICES=1: the tests run the multi-slot path -- worker threads, per-slot pools and streams, replicas --
+        // with two slots on the one GPU of a single-GPU box)
+        static const bool allow_dup = [] { const char* e = getenv("PCREG_ALLOW_DUP_DEVICES"); return e && e[0] == '1'; }();
+        for (int j = 0; j < k; ++j) PCREG_REQUIRE(allow_dup || devices[j] != dev, "pcreg_init: the same device listed twice");
+        PCREG_CUDA(cudaSetDevice(dev));
+        cudaDeviceProp p;
+        PCREG_CUDA(cudaGetDeviceProperties(&p, dev));
+        if (p.major < 10) {
+            set_error("pcreg_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, p.major, p.minor);
+            return PCREG_ERR_CUDA;
+        }
+        PCREG_CUDA(cudaFree(0));                        // create the context now, not inside the first timed call
+        Context& c = g_ctxs[k];
+        c = Context();
+        c.slot = k;
+        c.device = dev;
+        c.sm_count = p.multiProcessorCount;
+        c.smem_optin = p.sharedMemPerBlockOptin;
+        c.total_mem = p.totalGlobalMem;
+        c.initialised = true;
     }
-    Context& c = ctx();
-    c.device = dev;
-    c.sm_count = p.multiProcessorCount;
-    c.smem_optin = p.sharedMemPerBlockOptin;
-    c.total_mem = p.totalGlobalMem;
-    c.initialised = true;
+    g_nslots = n;
+    tl_slot = 0;
+    PCREG_CUDA(cudaSetDevice(g_ctxs[0].device));
     g_launches.store(0);
     return PCREG_OK;
     PCREG_API_END
 }
 
+int pcreg_device_count(void) { return g_nslots; }
+
 int pcreg_shutdown(void) {
-    if (ctx().initialised) {
+    for (int k = 0; k < g_nslots; ++k) {
+        Context& c = g_ctxs[k];
+        if (!c.initialised) continue;
+        cudaSetDevice(c.device);
         cudaDeviceSynchronize();
-        for (cudaEvent_t e : ctx().events) cudaEventDestroy(e);
-        ctx().events.clear();
+        for (cudaEvent_t e : c.events) cudaEventDestroy(e);
+        c.events.clear();
+        for (cudaStream_t st : c.streams) cudaStreamDestroy(st);
+        c.streams.clear();
         for (int b = 0; b < 2; ++b) {
-            if (ctx().pinned[b]) { cudaFreeHost(ctx().pinned[b]); ctx().pinned[b] = nullptr; }
-            if (ctx().pinned_ev[b]) { cudaEventDestroy(ctx().pinned_ev[b]); ctx().pinned_ev[b] = nullptr; }
+            if (c.pinned[b]) { cudaFreeHost(c.pinned[b]); c.pinned[b] = nullptr; }
+            if (c.pinned_ev[b]) { cudaEventDestroy(c.pinned_ev[b]); c.pinned_ev[b] = nullptr; }
         }
-        pool_trim(0);
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            pool_trim_locked(c, 0);
+        }
+        c.initialised = false;
     }
-    ctx().initialised = false;
+    g_nslots = 0;
+    tl_slot = 0;
     return PCREG_OK;
 }
 
-int pcreg_set_profiling(int enabled) { ctx().profiling = enabled != 0; ctx().profiling_counters = enabled != 2; return PCREG_OK; }
+int pcreg_set_profiling(int enabled) {
+    for (int k = 0; k < PCREG_MAX_DEVICES; ++k) { g_ctxs[k].profiling = enabled != 0; g_ctxs[k].profiling_counters = enabled != 2; }
+    return PCREG_OK;
+}
 int pcreg_last_profile(double out[32]) {
     if (!out) return PCREG_ERR_ARG;
     for (int i = 0; i < 32; ++i) out[i] = ctx().profile[i];
     return PCREG_OK;
 }
 
-int pcreg_model_create(const void* xyz, int is_double, int64_t n, int64_t ld, const pcreg_model_opts* opts, pcreg_model** out) {
-    PCREG_API_BEGIN
-    require_init();
-    PCREG_REQUIRE(xyz && out, "pcreg_model_create: null pointer");
-    PCREG_REQUIRE(n >= 1 && ld >= n, "pcreg_model_create: need n >= 1 and ld >= n");
-    PCREG_REQUIRE(n < ((int64_t)1 << 31) - BRUTE_TILE, "pcreg_model_create: model too large for int32 indices");
-    pcreg_model_opts o{};
-    if (opts) o = *opts;
-    PCREG_CUDA(cudaSetDevice(ctx().device));
+// one device-resident copy of the model on the calling thread's slot
+static pcreg_model* model_build_on_slot(const std::vector<ModelPointD>& h, const std::vector<int32_t>& perm, const double* lo,
+                                        const double* hi, float max_norm, const pcreg_model_opts& o) {
+    const int64_t n = (int64_t)h.size();
     std::unique_ptr<pcreg_model> m(new pcreg_model());
+    m->slot = current_slot();
     m->n = n;
     m->n_pad = ((n + BRUTE_TILE - 1) / BRUTE_TILE) * BRUTE_TILE;
-
-    // host staging: FP64 AoS in original order, bounding box, pivot, FP32 norm bound
-    std::vector<ModelPointD> h((size_t)n);
-    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int64_t i = 0; i < n; ++i) {
-        double v[3];
-        for (int a = 0; a < 3; ++a)
-            v[a] = is_double ? ((const double*)xyz)[a * ld + i] : (double)((const float*)xyz)[a * ld + i];
-        PCREG_REQUIRE(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]), "pcreg_model_create: non-finite model coordinate");
-        h[i].x = v[0]; h[i].y = v[1]; h[i].z = v[2]; h[i].pad = 0.0;
-        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], v[a]); hi[a] = std::max(hi[a], v[a]); }
-    }
-    double maxn2 = 0.0;
     for (int a = 0; a < 3; ++a) { m->bbox_lo[a] = lo[a]; m->bbox_hi[a] = hi[a]; m->pivot[a] = 0.5 * (lo[a] + hi[a]); }
-    for (int64_t i = 0; i < n; ++i) {
-        const float x = (float)(h[i].x - m->pivot[0]), y = (float)(h[i].y - m->pivot[1]), z = (float)(h[i].z - m->pivot[2]);
-        maxn2 = std::max(maxn2, (double)x * x + (double)y * y + (double)z * z);
-    }
-    m->max_norm = (float)(sqrt(maxn2) * (1.0 + 1e-6));
-    // scan-order permutation (Fisher-Yates, splitmix64)
-    std::vector<int32_t> perm((size_t)n);
-    for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
-    uint64_t s = o.shuffle_seed + 0x9E3779B97F4A7C15ull;
-    auto next = [&s]() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
-    for (int64_t i = n - 1; i > 0; --i) {
-        const int64_t j = (int64_t)(next() % (uint64_t)(i + 1));
-        std::swap(perm[i], perm[j]);
-    }
+    m->max_norm = max_norm;
     cudaStream_t st = 0;
     m->md.alloc((size_t)n);
     m->perm.alloc((size_t)m->n_pad);
@@ -494,14 +518,77 @@ int pcreg_model_create(const void* xyz, int is_double, int64_t n, int64_t ld, co
         vox_build(m.get(), o, st);
     }
     PCREG_CUDA(cudaStreamSynchronize(st));
-    *out = m.release();
+    return m.release();
+}
+
+int pcreg_model_create(const void* xyz, int is_double, int64_t n, int64_t ld, const pcreg_model_opts* opts, pcreg_model** out) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(xyz && out, "pcreg_model_create: null pointer");
+    PCREG_REQUIRE(n >= 1 && ld >= n, "pcreg_model_create: need n >= 1 and ld >= n");
+    PCREG_REQUIRE(n < ((int64_t)1 << 31) - BRUTE_TILE, "pcreg_model_create: model too large for int32 indices");
+    pcreg_model_opts o{};
+    if (opts) o = *opts;
+    use_slot(0);
+
+    // host staging: FP64 AoS in original order, bounding box, pivot, FP32 norm bound
+    std::vector<ModelPointD> h((size_t)n);
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = 0; i < n; ++i) {
+        double v[3];
+        for (int a = 0; a < 3; ++a)
+            v[a] = is_double ? ((const double*)xyz)[a * ld + i] : (double)((const float*)xyz)[a * ld + i];
+        PCREG_REQUIRE(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]), "pcreg_model_create: non-finite model coordinate");
+        h[i].x = v[0]; h[i].y = v[1]; h[i].z = v[2]; h[i].pad = 0.0;
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], v[a]); hi[a] = std::max(hi[a], v[a]); }
+    }
+    double maxn2 = 0.0, pivot[3];
+    for (int a = 0; a < 3; ++a) pivot[a] = 0.5 * (lo[a] + hi[a]);
+    for (int64_t i = 0; i < n; ++i) {
+        const float x = (float)(h[i].x - pivot[0]), y = (float)(h[i].y - pivot[1]), z = (float)(h[i].z - pivot[2]);
+        maxn2 = std::max(maxn2, (double)x * x + (double)y * y + (double)z * z);
+    }
+    const float max_norm = (float)(sqrt(maxn2) * (1.0 + 1e-6));
+    // scan-order permutation (Fisher-Yates, splitmix64)
+    std::vector<int32_t> perm((size_t)n);
+    for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
+    uint64_t s = o.shuffle_seed + 0x9E3779B97F4A7C15ull;
+    auto next = [&s]() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+    for (int64_t i = n - 1; i > 0; --i) {
+        const int64_t j = (int64_t)(next() % (uint64_t)(i + 1));
+        std::swap(perm[i], perm[j]);
+    }
+    // the model is replicated on every selected device: slots >= 1 build their copy on worker threads
+    const int ns = num_slots();
+    std::vector<pcreg_model*> copies((size_t)ns, nullptr);
+    std::vector<int> rc((size_t)ns, PCREG_OK);
+    std::vector<std::thread> workers;
+    for (int k = 1; k < ns; ++k)
+        workers.emplace_back([&, k]() { rc[k] = guarded([&]() { use_slot(k); copies[k] = model_build_on_slot(h, perm, lo, hi, max_norm, o); }); });
+    rc[0] = guarded([&]() { copies[0] = model_build_on_slot(h, perm, lo, hi, max_norm, o); });
+    for (auto& w : workers) w.join();
+    use_slot(0);
+    for (int k = 0; k < ns; ++k)
+        if (rc[k] != PCREG_OK) {
+            for (int j = 0; j < ns; ++j) if (copies[j]) { use_slot(j); cudaDeviceSynchronize(); delete copies[j]; }
+            use_slot(0);
+            return rc[k];
+        }
+    for (int k = 1; k < ns; ++k) copies[0]->replicas.push_back(copies[k]);
+    *out = copies[0];
     return PCREG_OK;
     PCREG_API_END
 }
 
 int pcreg_model_destroy(pcreg_model* m) {
     PCREG_API_BEGIN
-    if (m) { cudaDeviceSynchronize(); delete m; }
+    if (m) {
+        for (pcreg_model* r : m->replicas) { use_slot(r->slot); cudaDeviceSynchronize(); delete r; }
+        use_slot(m->slot);
+        cudaDeviceSynchronize();
+        delete m;
+        use_slot(0);
+    }
     return PCREG_OK;
     PCREG_API_END
 }

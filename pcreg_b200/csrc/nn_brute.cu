@@ -253,12 +253,9 @@ static void brute_run(const pcreg_model* m, BruteArgs a, const int32_t* d_prev, 
     const int64_t nq = a.nq;
     const int64_t qblocks = (nq + BRUTE_THREADS * Q - 1) / (BRUTE_THREADS * Q);
     const int slots = ctx().sm_count * 2;                  // co-resident blocks (2 per SM)
-    static bool attr_set = false;
-    if (!attr_set) {
-        PCREG_CUDA(cudaFuncSetAttribute(k_nn_brute<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRUTE_SMEM));
-        PCREG_CUDA(cudaFuncSetAttribute(k_nn_brute<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRUTE_SMEM));
-        attr_set = true;
-    }
+    // (function attributes are per device: set on every launch, it costs nothing next to the kernel)
+    PCREG_CUDA(cudaFuncSetAttribute(k_nn_brute<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRUTE_SMEM));
+    PCREG_CUDA(cudaFuncSetAttribute(k_nn_brute<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRUTE_SMEM));
     // Few query blocks: split the MODEL range so that all blocks fit in ONE wave with equal work
     // (split boundaries are multiples of the group size, not of the tile).  Many query blocks: no split.
     auto plan_split = [&](int64_t npts, int& nsplit, int64_t& len) {

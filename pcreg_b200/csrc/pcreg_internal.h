@@ -47,9 +47,24 @@ struct ArgError { std::string msg; };
     catch (const std::bad_alloc&) { ::pcreg::set_error("host allocation failed"); return PCREG_ERR_ALLOC; }   \
     catch (...) { ::pcreg::set_error("unknown C++ exception"); return PCREG_ERR_STATE; }
 
-// ---- library context (one device per process) -------------------------------------------------
+// Runs f on the calling thread and maps the library's exceptions to a status code (worker threads of the multi-device
+// entry points: no exception may leave a std::thread).
+template <typename F>
+int guarded(F&& f) {
+    PCREG_API_BEGIN
+    f();
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+// ---- library context: one per selected device ("slot" k = the k-th device handed to pcreg_init) ------
+// Host threads pick their slot with use_slot(); the thread that called pcreg_init works on slot 0, the
+// multi-device entry points (pcreg_icp_batch, pcreg_ransac_batch) run one worker thread per slot.
+constexpr int PCREG_MAX_DEVICES = 16;
+struct PoolBlock { void* p; size_t bytes; bool used; };
 struct Context {
     bool initialised = false;
+    int  slot = 0;
     int  device = 0;
     int  sm_count = 148;
     size_t smem_optin = 0;
@@ -61,7 +76,11 @@ struct Context {
     std::vector<cudaStream_t> streams;   // internal streams of the two-lane ICP loop
     void* pinned[2] = {nullptr, nullptr};   // bounce buffers of h2d_columns (allocated on first use)
     cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
+    std::vector<PoolBlock> pool;            // caching device allocator of this device
 };
+int  num_slots();                        // devices selected by pcreg_init
+void use_slot(int slot);                 // bind the calling host thread to a slot (+ cudaSetDevice)
+int  current_slot();
 cudaEvent_t pooled_event(size_t i);      // i-th reusable event, created on first use
 cudaStream_t lane_stream(int i);         // i-th internal stream (non-blocking), created on first use
 Context& ctx();
@@ -149,6 +168,9 @@ struct VoxView {                // passed by value to kernels
 }  // namespace pcreg
 
 struct pcreg_model {
+    int slot = 0;               // device slot this copy lives on
+    std::vector<pcreg_model*> replicas;     // slot-0 handle only: the copies on slots 1.. (replicas[k-1] = slot k)
+    const pcreg_model* on_slot(int k) const { return k == 0 ? this : replicas[(size_t)k - 1]; }
     int64_t n = 0;              // points
     int64_t n_pad = 0;          // padded to a multiple of the brute tile
     double pivot[3] = {0, 0, 0};        // subtracted before the FP32 conversion and before the 17 sums

@@ -10,7 +10,7 @@
 // to MATLAB's 1-based convention here.
 //
 // Commands (the matlab/*.m shims call these with the reference's own signatures):
-//   'init'[, device]                                   -> []
+//   'init'[, devices]                                  -> []      (scalar or vector of CUDA ordinals)
 //   'model_create', pts(Nx3 single|double)[, grid]     -> handle (uint64)
 //   'model_destroy', handle
 //   'nn_search', handle, q(Nx3)[, 'grid']              -> idx (Nx1 double, 1-based), d2 (Nx1)
@@ -46,10 +46,17 @@ std::string g_fail;                // set instead of throwing; reported after th
 
 void at_exit() { pcreg_shutdown(); g_init = false; }
 
-bool ensure_init(int device) {
+// devices: a MATLAB scalar or vector of CUDA ordinals (pcreg_mex('init', 0:7) drives eight GPUs from this one process)
+bool ensure_init(const mxArray* devices) {
     if (g_init) return true;
-    const int dev[1] = {device};
-    if (pcreg_init(dev, 1) != PCREG_OK) { g_fail = pcreg_last_error(); return false; }
+    int dev[16] = {0};
+    int nd = 1;
+    if (devices && !mxIsEmpty(devices)) {
+        nd = (int)mxGetNumberOfElements(devices);
+        if (nd > 16 || !mxIsDouble(devices)) { g_fail = "init: devices must be a double vector of at most 16 ordinals"; return false; }
+        for (int k = 0; k < nd; ++k) dev[k] = (int)mxGetPr(devices)[k];
+    }
+    if (pcreg_init(dev, nd) != PCREG_OK) { g_fail = pcreg_last_error(); return false; }
     mexLock();
     mexAtExit(at_exit);
     g_init = true;
@@ -406,9 +413,9 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
         if (nrhs < 1 || !mxIsChar(prhs[0]) || mxGetString(prhs[0], cmd, sizeof cmd) != 0) {
             g_fail = "pcreg_mex: first argument must be a command string";
         } else if (!strcmp(cmd, "init")) {
-            ok = ensure_init(nrhs > 1 ? (int)mxGetScalar(prhs[1]) : 0);
+            ok = ensure_init(nrhs > 1 ? prhs[1] : nullptr);
             if (ok && nlhs > 0) plhs[0] = empty();
-        } else if (!ensure_init(0)) {
+        } else if (!ensure_init(nullptr)) {
             ok = false;
         } else if (!strcmp(cmd, "model_create")) ok = cmd_model_create(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "model_destroy")) { pcreg_model_destroy(nrhs > 1 ? handle_of(prhs[1]) : nullptr); ok = true; if (nlhs > 0) plhs[0] = empty(); }

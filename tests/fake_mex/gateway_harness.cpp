@@ -94,7 +94,7 @@ int mexAtExit(void (*fn)(void)) { g_atexit = fn; return 0; }
 // stubs of the C ABI: record the arguments, return canned results
 // ---------------------------------------------------------------------------------------------------------
 struct Rec {
-    int init_dev = -1, inits = 0, shutdowns = 0;
+    int init_dev = -1, init_ndev = 0, init_last = -1, inits = 0, shutdowns = 0;
     int model_is_double = -1; int64_t model_n = 0, model_ld = 0; int model_grid = -1;
     int nn_kind = -1; int64_t nn_nq = 0; int nn_is_double = -1;
     int fail_next = 0;                          // next compute call returns PCREG_ERR_CUDA
@@ -113,7 +113,7 @@ static pcreg_model* const HANDLE = (pcreg_model*)(uintptr_t)0xABCD1234u;
 #define MAYBE_FAIL() do { if (R.fail_next) { R.fail_next = 0; return PCREG_ERR_CUDA; } } while (0)
 
 extern "C" {
-int pcreg_init(const int* devices, int ndev) { R.init_dev = ndev > 0 ? devices[0] : -1; ++R.inits; return PCREG_OK; }
+int pcreg_init(const int* devices, int ndev) { R.init_dev = ndev > 0 ? devices[0] : -1; R.init_ndev = ndev; R.init_last = ndev > 0 ? devices[ndev - 1] : -1; ++R.inits; return PCREG_OK; }
 int pcreg_shutdown(void) { ++R.shutdowns; return PCREG_OK; }
 const char* pcreg_last_error(void) { return "stub: device fell over"; }
 int pcreg_model_create(const void*, int is_double, int64_t n, int64_t ld, const pcreg_model_opts* o, pcreg_model** out) {
@@ -279,7 +279,7 @@ static bool is_empty00(const mxArray* a) { return a && a->cls == mxDOUBLE_CLASS 
 
 int main() {
     // ---- init: explicit device, mexLock once, atexit registered ----
-    { Out o = call(0, {str("init"), dbl(1, 1, {2})}); CHECK(o.err.empty()); CHECK(R.init_dev == 2 && R.inits == 1 && g_locks == 1 && g_atexit != nullptr); release(o); }
+    { Out o = call(0, {str("init"), dbl(1, 3, {2, 3, 5})}); CHECK(o.err.empty()); CHECK(R.init_dev == 2 && R.init_ndev == 3 && R.init_last == 5 && R.inits == 1 && g_locks == 1 && g_atexit != nullptr); release(o); }   // a device vector: one process drives several GPUs
     { Out o = call(0, {str("init")}); CHECK(R.inits == 1); release(o); }                              // second init is a no-op
 
     // ---- model_create: class single stays single, ld = n, grid by default; handle travels as uint64 ----
