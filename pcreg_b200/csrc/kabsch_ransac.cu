@@ -97,32 +97,54 @@ __device__ __forceinline__ void fit_accumulate(double* s, double w, const double
     s[26] += p2[1] * p2[1]; s[27] += p2[1] * p2[2]; s[28] += p2[2] * p2[2];
 }
 
-// rank of an n x 3 point matrix from its Gram matrix (singular values = sqrt of eigenvalues).
-// NOTE: for n > 3 this resolves singular values only down to ~1e-8 of the largest (documented
-// deviation from MATLAB's SVD-based rank on nearly degenerate clouds).
-__device__ __forceinline__ int rank_from_gram(const double* g6, long long n) {
+// rank(pts) >= need of an n x 3 point matrix (estimateTransform.m:11: MATLAB rank = singular values above
+// max(size) * eps(largest)).  The Gram matrix (summed in the same pass as the Kabsch sums) gives the singular values as
+// square roots of its eigenvalues, but only down to ~1e-8 of the largest.  Directions whose estimate is below 1e-6 of the
+// largest are therefore "uncertain": the caller measures them again DIRECTLY on the data -- sqrt(sum_i (p_i . v)^2) along the
+// Gram eigenvector v, a second pass over the points -- which resolves them to a few eps of the largest singular value,
+// the scale of MATLAB's own tolerance (tests/test_gpu_kabsch_ransac.py brackets the agreement).
+struct RankProbe {
+    double V[9];        // eigenvectors of the Gram matrix (columns)
+    double smax, tol;   // largest singular value, MATLAB's tolerance
+    int sure;           // directions certainly above the tolerance
+    int uncertain[3];   // columns of V to measure again
+    int nunc;
+};
+__device__ __forceinline__ void rank_probe(const double* g6, long long n, RankProbe& r) {
     double A[9] = {g6[0], g6[1], g6[2], g6[1], g6[3], g6[4], g6[2], g6[4], g6[5]};
-    double w[3], V[9];
-    eigsym3(A, w, V);
+    double w[3];
+    eigsym3(A, w, r.V);
     double sv[3];
     for (int k = 0; k < 3; ++k) sv[k] = w[k] > 0.0 ? sqrt(w[k]) : 0.0;
-    double smax = fmax(sv[0], fmax(sv[1], sv[2]));
-    // eigenvalues of the Gram matrix carry an absolute error ~ eps * smax^2
-    const double floor_sv = smax * 1.5e-8;
-    const double tol = fmax((double)(n > 3 ? n : 3) * spacing(smax), floor_sv);
-    return (sv[0] > tol) + (sv[1] > tol) + (sv[2] > tol);
+    r.smax = fmax(sv[0], fmax(sv[1], sv[2]));
+    r.tol = (double)(n > 3 ? n : 3) * spacing(r.smax);
+    r.sure = 0; r.nunc = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (sv[k] > 1.0e-6 * r.smax && sv[k] > r.tol) ++r.sure;
+        else r.uncertain[r.nunc++] = k;
+    }
+}
+// squared projections of one point on the uncertain directions (accumulated by the caller, then reduced)
+__device__ __forceinline__ void rank_refine_accumulate(const RankProbe& r, const double* p, double* acc /*[3]*/) {
+    for (int u = 0; u < r.nunc; ++u) {
+        const int k = r.uncertain[u];
+        const double t = p[0] * r.V[0 * 3 + k] + p[1] * r.V[1 * 3 + k] + p[2] * r.V[2 * 3 + k];
+        acc[u] += t * t;
+    }
+}
+__device__ __forceinline__ int rank_final(const RankProbe& r, const double* acc) {
+    int rank = r.sure;
+    for (int u = 0; u < r.nunc; ++u) rank += (sqrt(acc[u]) > r.tol) ? 1 : 0;
+    return rank;
 }
 
-__device__ __forceinline__ int fit_from_sums(const double* s, long long n, const double* piv1, const double* piv2,
-                                             bool reflection_fix, double* T) {
-    if (rank_from_gram(s + 17, n) < 3 || rank_from_gram(s + 23, n) < 2) return 1;
+__device__ __forceinline__ void kabsch_from_fit_sums(const double* s, const double* piv1, const double* piv2, bool reflection_fix, double* T) {
     KabschSums ks;
     ks.sw = s[0];
     for (int k = 0; k < 3; ++k) { ks.sq[k] = s[1 + k]; ks.sm[k] = s[4 + k]; }
     for (int k = 0; k < 9; ++k) ks.sqm[k] = s[7 + k];
     ks.swd2 = 0.0;
     kabsch_from_sums(ks, piv2, piv1, reflection_fix, T);
-    return 0;
 }
 
 // ---- pcreg_kabsch_batch: one block per problem ----------------------------------------------------
@@ -155,7 +177,27 @@ __global__ void __launch_bounds__(128) k_kabsch_batch(const double* __restrict__
             fit_accumulate(s, w ? w[r0 + i] : 1.0, a, c, piv1, piv2);
         }
         block_sum<NS_FIT>(s, red);
-        if (tid == 0) st = (s[0] > 0.0) ? fit_from_sums(s, n, piv1, piv2, reflection_fix != 0, T) : 1;
+        // rank guard (estimateTransform.m:11-14): every thread holds the reduced sums, so the probes are block-uniform
+        RankProbe r1, r2;
+        rank_probe(s + 17, n, r1);
+        rank_probe(s + 23, n, r2);
+        int rank1 = r1.sure, rank2 = r2.sure;
+        if ((r1.sure < 3 && r1.nunc > 0) || (r2.sure < 2 && r2.nunc > 0)) {       // uncertain directions decide: measure them on the data
+            double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int64_t i = tid; i < n; i += blockDim.x) {
+                const double a[3] = {p1[r0 + i], p1[ld + r0 + i], p1[2 * ld + r0 + i]};
+                const double c[3] = {p2[r0 + i], p2[ld + r0 + i], p2[2 * ld + r0 + i]};
+                rank_refine_accumulate(r1, a, acc);
+                rank_refine_accumulate(r2, c, acc + 3);
+            }
+            block_sum<6>(acc, red);
+            rank1 = rank_final(r1, acc);
+            rank2 = rank_final(r2, acc + 3);
+        }
+        if (tid == 0) {
+            st = (s[0] > 0.0 && rank1 >= 3 && rank2 >= 2) ? 0 : 1;
+            if (st == 0) kabsch_from_fit_sums(s, piv1, piv2, reflection_fix != 0, T);
+        }
     }
     if (tid == 0) {
         status[b] = st;
@@ -258,7 +300,26 @@ __global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ Ra
                     }
 #pragma unroll
                     for (int k = 0; k < NS_FIT; ++k) s[k] = warp_sum(s[k]);
-                    st2 = fit_from_sums(s, cnt, piv1, piv2, g.reflection_fix != 0, T2);
+                    RankProbe r1, r2;                                            // rank guard of the refit (estimateTransform.m:11-14)
+                    rank_probe(s + 17, cnt, r1);
+                    rank_probe(s + 23, cnt, r2);
+                    int rank1 = r1.sure, rank2 = r2.sure;
+                    if ((r1.sure < 3 && r1.nunc > 0) || (r2.sure < 2 && r2.nunc > 0)) {
+                        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                        for (int64_t i = lane; i < a.P; i += 32) {
+                            double x[3], y[3], qx, qy, qz;
+                            load_pt(a.p1, a.ld, i, x);
+                            load_pt(a.p2, a.ld, i, y);
+                            quick_tf(T1, y[0], y[1], y[2], qx, qy, qz);
+                            if (dist2_exact(x[0], x[1], x[2], qx, qy, qz) < a.thDist) { rank_refine_accumulate(r1, x, acc); rank_refine_accumulate(r2, y, acc + 3); }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+                        rank1 = rank_final(r1, acc);
+                        rank2 = rank_final(r2, acc + 3);
+                    }
+                    st2 = (rank1 >= 3 && rank2 >= 2) ? 0 : 1;
+                    if (st2 == 0) kabsch_from_fit_sums(s, piv1, piv2, g.reflection_fix != 0, T2);
                 }
                 if (st2 == 0) {
                     cnt_ref = warp_count_inliers(a, T2, lane);                  // :56-58

@@ -430,7 +430,8 @@ int pcreg_init(const int* devices, int ndev) {
         PCREG_REQUIRE(dev >= 0 && dev < count, "pcreg_init: device ordinal out of range");
         // (PCREG_ALLOW_DUP_DEVICES=1: the tests run the multi-slot path -- worker threads, per-slot pools and streams, replicas --
         // with two slots on the one GPU of a single-GPU box)
-        static const bool allow_dup = [] { const char* e = getenv("PCREG_ALLOW_DUP_DEVICES"); return e && e[0] == '1'; }();
+        const char* dup_e = getenv("PCREG_ALLOW_DUP_DEVICES");
+        const bool allow_dup = dup_e && dup_e[0] == '1';
         for (int j = 0; j < k; ++j) PCREG_REQUIRE(allow_dup || devices[j] != dev, "pcreg_init: the same device listed twice");
         PCREG_CUDA(cudaSetDevice(dev));
         cudaDeviceProp p;

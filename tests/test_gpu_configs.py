@@ -65,3 +65,83 @@ def test_config5_16m_model_grid_search(pcreg):
     assert np.all(res["n_used"] == oracle.matlab_round(0.85 * 65_536))   # AlignPoints_KNN.m:20-21
     # values cross-checked with the oracle composition (kd-tree, 76 s on 8 cores): alignment error 0.028-0.058, rmse 0.17-0.19
     assert oracle.check_alignment(res["T"][res["best"]][:3, :3], T_gt[:3, :3]) < 0.06 and res["rmse"].max() < 0.21
+
+
+def _edge_hypotheses(w):
+    """indices into bench.make_inputs' pose grid (rotation-major, then x, y, z): corners of the translation lattice under
+    the first, a middle and the last rotations -- the hypotheses that start farthest from the optimum"""
+    nx, ny, nz = w["trans"]
+    out = []
+    for r, (x, y, z) in zip((w["rot"] - 1, w["rot"] - 1, w["rot"] // 2, w["rot"] // 2, 1, 1, w["rot"] - 2, 2),
+                            ((0, 0, 0), (nx - 1, ny - 1, nz - 1), (0, ny - 1, 0), (nx - 1, 0, nz - 1), (0, 0, nz - 1), (nx - 1, ny - 1, 0),
+                             (0, ny - 1, nz - 1), (nx - 1, 0, 0))):
+        out.append(((r * nx + x) * ny + y) * nz + z)
+    return np.array(out)
+
+
+def test_config3_full_size_vs_oracle_and_brute(pcreg):
+    """BASELINE.json configs[2] exactly as bench.py runs it (1 M-point model, 5 000 source points, 4096-pose grid of 20 deg /
+    2 mm, KNN trim, 30 iterations, seed 1003): eight hypotheses from the EDGES of the pose grid against the oracle
+    composition, and 128 hypotheses spread over the grid grid-path == brute-force path bit for bit."""
+    import bench
+    w = bench.WORKLOADS["c3"]
+    model, src, T0, w_src, T_gt = bench.make_inputs(w, 0)
+    assert model.shape[0] == 1_000_000 and src.shape[0] == 5000 and T0.shape[0] == 4096
+    sel = _edge_hypotheses(w)
+    ref = oracle.icp_batch(model, src, T0[sel], mode=oracle.ICP_KNN, iters=30, k_frac=0.85, return_hist=True)
+    m = pcreg.Model(model, grid=True)
+    assert m.voxel_info()["voxels"] > 0                      # the path bench.py measures: Voronoi voxel map + fused kernel
+    res = pcreg.icp_batch(m, src, T0[sel], mode=pcreg.ICP_KNN, iters=30, k_frac=0.85, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    _compare(res, ref)
+    for h in range(sel.size):
+        np.testing.assert_allclose(res["rmse_hist"][h], ref["results"][h]["rmse_hist"], rtol=1e-7)
+    many = np.arange(0, 4096, 32)                            # 128 hypotheses over the whole grid
+    a = pcreg.icp_batch(m, src, T0[many], mode=pcreg.ICP_KNN, iters=30, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    b = pcreg.icp_batch(m, src, T0[many], mode=pcreg.ICP_KNN, iters=30, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    # the same batch through the grid kernels of models WITHOUT a voxel map (pyramid walk, row scan, candidate lists)
+    m2 = pcreg.Model(model, grid=True, voxel_map=-1)
+    c2 = pcreg.icp_batch(m2, src, T0[many[:32]], mode=pcreg.ICP_KNN, iters=30, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(c2[k], b[k][:32]), k
+    m.destroy(); m2.destroy()
+
+
+def test_config2_full_size_vs_oracle(pcreg):
+    """BASELINE.json configs[1] as bench.py runs it: one AlignPoints_weighted-style alignment, 10 000 weighted source points
+    vs a 500 k-point model, 100 iterations -- brute force and grid NN against the oracle composition."""
+    import bench
+    w = bench.WORKLOADS["c2"]
+    model, src, T0, w_src, T_gt = bench.make_inputs(w, 0)
+    assert model.shape[0] == 500_000 and src.shape[0] == 10_000 and T0.shape[0] == 1 and w_src is not None
+    ref = oracle.icp_batch(model, src, T0, mode=oracle.ICP_WEIGHTED, iters=100, R_w=3.5, w_src=w_src, return_hist=True)
+    m = pcreg.Model(model, grid=True)
+    for nn in (pcreg.NN_BRUTE, pcreg.NN_GRID):
+        res = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_WEIGHTED, iters=100, R_w=3.5, w_src=w_src, nn=nn, return_idx=True, return_hist=True)
+        _compare(res, ref)
+        np.testing.assert_allclose(res["rmse_hist"][0], ref["results"][0]["rmse_hist"], rtol=1e-7)
+    m.destroy()
+
+
+def test_config5_bench_shape_wide_starts(pcreg):
+    """C5 at the shape bench.py --workload c5 runs (16 M-point model, 65 536 source points, the 10 deg / 2 mm pose grid):
+    64 hypotheses spread over the grid, including its edges -- wide search balls that exercise the warp-per-query walk, its
+    overflow hand-off and the extension pool of the candidate lists.  Grid path == brute-force path bit for bit on the four
+    farthest starts; determinism and the trim count on all 64."""
+    import bench
+    w = bench.WORKLOADS["c5"]
+    model, src, T0, w_src, T_gt = bench.make_inputs(w, 0)
+    assert model.shape[0] == 16_000_000 and src.shape[0] == 65_536
+    sel = np.unique(np.concatenate([_edge_hypotheses(w), np.arange(0, T0.shape[0], T0.shape[0] // 56)]))[:64]
+    m = pcreg.Model(model, grid=True)
+    a = pcreg.icp_batch(m, src, T0[sel], mode=pcreg.ICP_KNN, iters=20, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    a2 = pcreg.icp_batch(m, src, T0[sel], mode=pcreg.ICP_KNN, iters=20, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k], a2[k]), k
+    far = np.argsort(-a["rmse_hist"][:, 0])[:4]              # the four starts with the largest initial residual
+    b = pcreg.icp_batch(m, src, T0[sel][far], mode=pcreg.ICP_KNN, iters=20, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k][far], b[k]), k
+    assert np.all(a["n_used"] == oracle.matlab_round(0.85 * 65_536)) and np.all(np.isfinite(a["rmse"]))
+    m.destroy()

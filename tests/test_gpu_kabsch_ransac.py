@@ -51,6 +51,35 @@ def test_estimate_transform_rank_guard_returns_empty(pcreg):
     assert pcreg.estimateTransform(three_coplanar_with_origin, full[:3]) is None
 
 
+def test_rank_guard_tracks_matlab_rank_on_nearly_degenerate_clouds(pcreg):
+    """estimateTransform.m:11 uses MATLAB's SVD-based rank (tolerance max(size) * eps(largest singular value)) on the RAW
+    point matrices.  The kernel finds the large singular values from the Gram matrix and measures the small ones again
+    directly on the data, so it must agree with oracle.matlab_rank while the third singular value of pts1 (the second of
+    pts2) sweeps from 1e-3 down to 1e-14 of the first -- everywhere except within a factor 8 of the tolerance itself, where
+    MATLAB's own rounding decides."""
+    g = synth.rng(42)
+    for n in (4, 9, 60, 700):
+        U, _ = np.linalg.qr(g.normal(0, 1, (n, 3)))
+        V, _ = np.linalg.qr(g.normal(0, 1, (3, 3)))
+        full = g.normal(0, 30, (n, 3)) + np.array([40.0, -20.0, 70.0])
+        eps = np.finfo(np.float64).eps
+        for ratio in (1e-3, 1e-6, 1e-8, 1e-10, 1e-12, 1e-13, 1e-14, 1e-15, 1e-17, 0.0):
+            tol_ratio = n * eps                                          # MATLAB's tolerance relative to the largest singular value
+            decided = ratio > 8 * tol_ratio or ratio < tol_ratio / 8
+            # pts1 nearly rank 2 (third singular value = ratio * first)
+            p1 = (U * np.array([100.0, 37.0, 100.0 * ratio])) @ V.T
+            want = oracle.estimateTransform(p1, full)
+            got = pcreg.estimateTransform(p1, full)
+            if decided:
+                assert (want is None) == (got is None), ("pts1", n, ratio, oracle.matlab_rank(p1))
+            # pts2 nearly rank 1 (second singular value = ratio * first)
+            p2 = (U * np.array([100.0, 100.0 * ratio, 0.0])) @ V.T
+            want = oracle.estimateTransform(full, p2)
+            got = pcreg.estimateTransform(full, p2)
+            if decided:
+                assert (want is None) == (got is None), ("pts2", n, ratio, oracle.matlab_rank(p2))
+
+
 def test_reflection_default_is_reference_behaviour(pcreg):
     """R = V*U' with no determinant check (estimateTransform.m:62); the fix is a switch."""
     g = synth.rng(4)
