@@ -280,6 +280,7 @@ int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
  *   out[17..19] = total ms and out[20..22] = launches of the list-scan / row-scan / walk kernels,
  *   out[23] = queries whose search was skipped by lazy trimming (they are included in out[10]);
  *   after pcreg_get_matches: out[24] = total ms of the score kernel, out[25] = (pair, dimension) terms it evaluated;
+ *   after pcreg_align_points: out[24] = ms of the alignment kernel, out[25] = points it processed;
  *   out[26] = 1 when the grid NN ran on the model's Voronoi voxel map: then out[10] = queries answered by the voxel list
  *   scan, out[13] = list entries read, out[14] = points gathered for the FP64 decision, out[17] / out[20] = ms / launches
  *   of the list-scan kernel, and out[11], out[15], out[16], out[9], out[19] describe the pyramid walk of the rest.

@@ -306,14 +306,25 @@ int pcreg_align_points(int kind, const void* pts, int is_double, int64_t ld, con
     a.kind = kind; a.pts = d_in.p; a.is_double = is_double; a.ld = (int64_t)nel; a.offsets = d_off.p;
     a.k_frac = o.k_frac; a.k_abs = o.k_abs; a.R_w = o.R_w; a.r_local = o.r_local; a.min_local = o.min_local; a.C1 = o.C1; a.C2 = o.C2;
     a.out = d_out.p; a.coeff9 = d_coeff.p; a.c3 = d_c.p; a.status = d_st.p; a.keys = d_keys.p;
+    const bool prof = ctx().profiling;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) { e0 = pooled_event(0); e1 = pooled_event(1); PCREG_CUDA(cudaEventRecord(e0, st)); }
     k_align_points<<<(unsigned)nbatch, ALIGN_THREADS, 0, st>>>(a);
     PCREG_LAUNCHED();
+    if (prof) PCREG_CUDA(cudaEventRecord(e1, st));
     for (int k = 0; k < 3; ++k)
         PCREG_CUDA(cudaMemcpyAsync((unsigned char*)pts_aligned + (size_t)k * ld * el, d_out.p + k * nel * el, (size_t)ntotal * el, cudaMemcpyDeviceToHost, st));
     PCREG_CUDA(cudaMemcpyAsync(coeff9, d_coeff.p, d_coeff.bytes(), cudaMemcpyDeviceToHost, st));
     PCREG_CUDA(cudaMemcpyAsync(c3, d_c.p, d_c.bytes(), cudaMemcpyDeviceToHost, st));
     PCREG_CUDA(cudaMemcpyAsync(status, d_st.p, d_st.bytes(), cudaMemcpyDeviceToHost, st));
     PCREG_CUDA(cudaStreamSynchronize(st));
+    if (prof) {                                          // pcreg_last_profile: out[24] = kernel ms, out[25] = points
+        float ms = 0.f;
+        PCREG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        Context& c = ctx();
+        for (int i = 0; i < 32; ++i) c.profile[i] = 0.0;
+        c.profile[24] = ms; c.profile[25] = (double)ntotal;
+    }
     return PCREG_OK;
     PCREG_API_END
 }

@@ -36,18 +36,26 @@ def pack_records(T, rmse, n_used, status, per: int, device) -> torch.Tensor:
     return rec
 
 
-def first_argmin(rmse: torch.Tensor) -> int:
-    """First index of the minimum, NaN never wins; -1 if everything is NaN."""
-    ok = ~torch.isnan(rmse)
-    if not bool(ok.any()):
-        return -1
-    v = torch.where(ok, rmse, torch.full_like(rmse, float("inf")))
+def first_argmin_t(rmse: torch.Tensor) -> torch.Tensor:
+    """First index of the minimum as a 0-d int64 tensor ON THE DEVICE (no host synchronisation): NaN never wins,
+    -1 if everything is NaN."""
+    n = rmse.shape[0]
+    v = torch.where(torch.isnan(rmse), torch.full_like(rmse, float("inf")), rmse)
     m = v.min()
-    return int(torch.nonzero(v == m)[0, 0])
+    ar = torch.arange(n, dtype=torch.int64, device=rmse.device)
+    cand = torch.where(v == m, ar, torch.full_like(ar, n))                 # ties -> smallest index
+    best = cand.min()
+    return torch.where(torch.isinf(m), torch.full_like(best, -1), best)
 
 
-def gather_and_pick(rec_local: torch.Tensor, nhyp: int, per: int, group=None):
-    """all_gather the per-rank records and pick the winner.  Returns (records [nhyp, RECORD], best)."""
+def first_argmin(rmse: torch.Tensor) -> int:
+    """First index of the minimum, NaN never wins; -1 if everything is NaN (one host read)."""
+    return int(first_argmin_t(rmse))
+
+
+def gather_and_pick(rec_local: torch.Tensor, nhyp: int, per: int, group=None, on_device=False):
+    """all_gather the per-rank records and pick the winner.  Returns (records [nhyp, RECORD], best); with on_device the
+    winner stays a 0-d device tensor, so the step queues no host synchronisation of its own."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > 1:
         allrec = torch.empty((world * per, RECORD), dtype=torch.float64, device=rec_local.device)
@@ -55,7 +63,8 @@ def gather_and_pick(rec_local: torch.Tensor, nhyp: int, per: int, group=None):
     else:
         allrec = rec_local
     allrec = allrec[:nhyp]
-    return allrec, first_argmin(allrec[:, 0])
+    best = first_argmin_t(allrec[:, 0])
+    return allrec, (best if on_device else int(best))
 
 
 def icp_batch_sharded(local_fn, T0s, group=None, device="cpu"):
