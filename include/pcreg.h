@@ -81,8 +81,10 @@ int64_t pcreg_model_size(const pcreg_model* m);
 /* Grid facts for roofline accounting: dims[3], cell size, number of non-empty level-0 cells. */
 int  pcreg_model_grid_info(const pcreg_model* m, int32_t dims[3], double* cell_size, int64_t* occupied);
 /* Voxel-map facts (all zero when the model has none): dims[3], voxel edge, stats = {voxels, voxels with a list, entries,
- * voxels without a list because it was too long, ... because the pool was full, longest list, build time in us, bytes}. */
-int  pcreg_model_voxel_info(const pcreg_model* m, int32_t dims[3], double* voxel_size, int64_t stats[8]);
+ * voxels without a list because it was too long, ... because the pool was full, longest list, build time in us, bytes,
+ * voxels without a list because they lie outside the band, band width in 1e-6 model units (0: no band -- every voxel of
+ * the padded box has a list; dense models get a band-limited map: only voxels near the model are listed)}. */
+int  pcreg_model_voxel_info(const pcreg_model* m, int32_t dims[3], double* voxel_size, int64_t stats[10]);
 
 /* ---- nearest neighbour (knnsearch(model, q, 'K', 1) semantics: Euclidean, FP64, ties -> smallest
  *      index; the reference's only literal cloud->cloud 1-NN loop is ColorCodeModel.m:15-18) ---- */

@@ -87,10 +87,10 @@ class Model:
         """Voronoi voxel map facts (dims all zero when the model has none)."""
         dims = (C.c_int32 * 3)()
         vs = C.c_double()
-        st = (C.c_int64 * 8)()
+        st = (C.c_int64 * 10)()
         L.check(L.lib().pcreg_model_voxel_info(self.handle, dims, C.byref(vs), st), "pcreg_model_voxel_info")
         return dict(dims=tuple(dims), voxel_size=vs.value, voxels=st[0], listed=st[1], entries=st[2], too_long=st[3],
-                    no_room=st[4], max_len=st[5], build_ms=st[6] / 1000.0, bytes=st[7])
+                    no_room=st[4], max_len=st[5], build_ms=st[6] / 1000.0, bytes=st[7], outside_band=st[8], band=st[9] * 1e-6)
 
     def nn_search(self, q, nn: int = NN_BRUTE):
         """knnsearch(model, q, 'K', 1): returns (idx int32 [nq] 0-based, d2 float64 [nq] squared distance)."""

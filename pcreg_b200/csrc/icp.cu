@@ -374,7 +374,7 @@ static void icp_run(const pcreg_model* m, const double* d_src /*col-major ns x 3
     const double t_enter = now_ms();
     double t_alloc = 0, t_sorted = 0, t_enq = 0;
 
-    const bool fused = icp_fused_eligible(m, ns, o);
+    const bool fused = icp_fused_eligible(m, ns, nhyp, o);
     // chunk the hypotheses so that the per-correspondence scratch stays bounded
     const size_t total_b = c.total_mem;         // queried once at pcreg_init (cudaMemGetInfo costs up to tens of ms per call)
     const size_t per_hyp = (size_t)ns * (4 + 4 + 8 + (o.mode == PCREG_ICP_KNN ? 8 : 0) + (o.nn == PCREG_NN_GRID ? 8 + (m->has_vox ? 0 : 28 + 4 * 64 + 4 * 448 / 16) : 0));

@@ -206,9 +206,12 @@ size_t icp_fused_smem(int64_t ns, int mode) {
     return (((size_t)ns * 4 + 15) / 16) * 16 + (mode == PCREG_ICP_KNN ? (size_t)ns * 8 : 0);
 }
 
-bool icp_fused_eligible(const pcreg_model* m, int64_t ns, const pcreg_icp_opts& o) {
+bool icp_fused_eligible(const pcreg_model* m, int64_t ns, int64_t nhyp, const pcreg_icp_opts& o) {
     if (!m->has_vox || o.nn != PCREG_NN_GRID) return false;
-    if (const char* e = getenv("PCREG_FUSED")) { if (e[0] == '0') return false; }
+    if (const char* e = getenv("PCREG_FUSED")) { if (e[0] == '0') return false; if (e[0] == '1') nhyp = (int64_t)1 << 40; }
+    // one block per hypothesis: a batch smaller than the SM count leaves SMs idle, the per-pass kernels (all SMs on every
+    // pass) are faster there (C2, one hypothesis: 13.9 ms fused vs the per-pass path; PCREG_FUSED=1 forces the fused kernel)
+    if (nhyp < ctx().sm_count) return false;
     if (ns >= ((int64_t)1 << 30)) return false;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k_icp_fused) != cudaSuccess) { cudaGetLastError(); return false; }

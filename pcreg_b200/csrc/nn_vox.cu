@@ -55,7 +55,9 @@ struct VoxLevelArgs {
     unsigned long long* work_cursor;            // next unassigned parent slot
     double origin[3]; double cs;                // child voxel edge
     uint32_t maxlen;
-    unsigned long long* stats;                  // [0] listed voxels, [1] entries, [2] dropped: too long, [3] dropped: no room, [4] longest list
+    float band;                                 // > 0: voxels farther than this from the model get no list (band-limited map of a dense model)
+    unsigned long long* stats;                  // [0] listed voxels, [1] entries, [2] dropped: too long, [3] dropped: no room, [4] longest list,
+                                                // [5] dropped: outside the band
 };
 
 struct Pivots { float x[9], y[9], z[9], n[9]; };
@@ -138,6 +140,12 @@ __global__ void __launch_bounds__(256) k_vox_top(const __grid_constant__ VoxLeve
     for (int j = 0; j < 9; ++j) best[j] = s_piv[j];
     Pivots pv;
     load_pivots(a.pts, best, ccx, ccy, ccz, pv);
+    // pivot 0 is the model point nearest to the voxel centre: a voxel that lies wholly farther than `band` from the model is
+    // left without a list (its queries are walked) -- block-uniform
+    if (a.band > 0.f && sqrtf(pv.n[0]) - 1.7320509f * e > a.band) {
+        if (tid == 0) { a.c_hdr[brick_index(cx, cy, cz, a.ct)] = make_uint2(0u, VOX_DROPPED); atomicAdd(&a.stats[5], 1ull); }
+        return;
+    }
     // pass 2: count
     unsigned int cnt = 0;
     for (uint32_t t = tid; t < a.npts; t += 256) {
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(256) k_vox_refine(const __grid_constant__ VoxL
     const unsigned lt = (1u << lane) - 1u;
     const int64_t nslots = (int64_t)a.pt[0] * a.pt[1] * a.pt[2] * 64;
     unsigned long long w_off = 0, w_end = 0;                               // pool range reserved by this warp
-    unsigned long long st_listed = 0, st_entries = 0, st_long = 0, st_room = 0, st_max = 0;
+    unsigned long long st_listed = 0, st_entries = 0, st_long = 0, st_room = 0, st_max = 0, st_far = 0;
     const float e = (float)(0.5 * a.cs * (1.0 + 1e-4));
     const float tol_abs = 1e-6f * e * e;
 
@@ -252,6 +260,11 @@ __global__ void __launch_bounds__(256) k_vox_refine(const __grid_constant__ VoxL
                 }
                 Pivots pv;
                 load_pivots(a.pts, best, ccx, ccy, ccz, pv);
+                if (a.band > 0.f && sqrtf(pv.n[0]) - 1.7320509f * e > a.band) {       // wholly outside the band (see k_vox_top)
+                    if (lane == 0) a.c_hdr[ci] = make_uint2(0u, FINAL ? 0u : VOX_DROPPED);
+                    ++st_far;
+                    continue;
+                }
                 // sweep 2: count (the keep flags of the first 32 rounds are remembered)
                 uint32_t cnt = 0, flags = 0;
                 for (uint32_t it = 0; it < nit; ++it) {
@@ -315,6 +328,7 @@ __global__ void __launch_bounds__(256) k_vox_refine(const __grid_constant__ VoxL
         if (st_long) atomicAdd(&a.stats[2], st_long);
         if (st_room) atomicAdd(&a.stats[3], st_room);
         if (st_max) atomicMax(&a.stats[4], st_max);
+        if (st_far) atomicAdd(&a.stats[5], st_far);
     }
 }
 
@@ -374,7 +388,7 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
     double s = scale * delta;
     if (!(s > 0.0) || !std::isfinite(s)) return;
     const double margin = o.voxel_margin > 0.0 ? o.voxel_margin : (o.voxel_margin < 0.0 ? 0.0 : env_double("PCREG_VOX_MARGIN", 0.04) * maxext);
-    const size_t budget_bytes = c.total_mem / 8;                      // header + entries of the finest level
+    const size_t budget_bytes = c.total_mem / 8;                      // entries of the finest level
     const double max_vox = (double)(o.max_voxels > 0 ? o.max_voxels : std::min<int64_t>((int64_t)1 << 27, (int64_t)(budget_bytes / 128)));
     int32_t dims[3];
     auto size_for = [&](double edge) {
@@ -383,9 +397,30 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         return tot;
     };
     double nv = size_for(s);
-    while (nv > max_vox) { s *= std::max(1.02, cbrt(nv / max_vox)); nv = size_for(s); }
-    // too dense for the budget: the lists would hold hundreds of points -- leave such models to the grid kernels
-    if (s > 3.5 * delta && o.voxel_map != 1) return;
+    double band = 0.0;                                                // 0: every voxel of the padded box gets a list
+    int base_cap = (int)std::max(8.0, env_double("PCREG_VOX_CAP", (double)VOX_BASE_CAP));
+    if (nv > max_vox && o.voxel_map != 1 && o.max_voxels <= 0) {
+        // Dense model (C5: 16 M points, 0.04 mm spacing): a map over the whole box does not fit.  ICP queries live near the
+        // surface, so only the voxels within `band` of the model get lists (about max_vox of them); the header array stays
+        // dense (8 B per voxel), queries beyond the band are walked.  Voxels of 2.5 spacings: lists of ~30 entries.
+        const double s_band = std::max(s, env_double("PCREG_VOX_DENSE_SCALE", 2.5) * delta);
+        const double hdr_budget = (double)c.total_mem / 16.0 / 8.0;            // voxels whose headers fit in 1/16 of the memory
+        double sb = s_band;
+        double nvb = size_for(sb);
+        while (nvb > hdr_budget && sb < 6.0 * delta) { sb *= 1.05; nvb = size_for(sb); }
+        const double area = occ * cell * cell;
+        const double b = max_vox * sb * sb * sb / (2.0 * area);                 // slab of +- band around the surface holds ~max_vox voxels
+        if (nvb <= hdr_budget && b >= 4.0 * sb) {
+            s = sb; nv = nvb; band = std::min(b, maxext);
+            base_cap = std::max(base_cap, 192);
+        }
+    }
+    if (band == 0.0 && env_double("PCREG_VOX_BAND", 0.0) > 0.0) band = env_double("PCREG_VOX_BAND", 0.0);      // tests: force a band
+    else if (band == 0.0) {
+        while (nv > max_vox) { s *= std::max(1.02, cbrt(nv / max_vox)); nv = size_for(s); }
+        // too dense for the budget: the lists would hold hundreds of points -- leave such models to the grid kernels
+        if (s > 3.5 * delta && o.voxel_map != 1) return;
+    }
     std::vector<std::array<int32_t, 3>> ld;
     ld.push_back({dims[0], dims[1], dims[2]});
     while (std::max({ld.back()[0], ld.back()[1], ld.back()[2]}) > VOX_TOP_DIM)
@@ -395,11 +430,10 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         ld.push_back({(dims[0] + 1) / 2, (dims[1] + 1) / 2, (dims[2] + 1) / 2});
     }
     const int L = (int)ld.size();
-    const int base_cap = (int)std::max(8.0, env_double("PCREG_VOX_CAP", (double)VOX_BASE_CAP));
 
     cudaEvent_t e0 = pooled_event(0), e1 = pooled_event(1);
     PCREG_CUDA(cudaEventRecord(e0, st));
-    DevBuf<unsigned long long> ctrl(8);                               // [0] pool cursor, [1] work cursor, [2..6] stats
+    DevBuf<unsigned long long> ctrl(8);                               // [0] pool cursor, [1] work cursor, [2..7] stats
     auto tiles_of = [](const std::array<int32_t, 3>& d, int32_t* t) { for (int a = 0; a < 3; ++a) t[a] = (d[a] + 3) / 4; };
     auto slots_of = [&](const std::array<int32_t, 3>& d) { int32_t t[3]; tiles_of(d, t); return (size_t)t[0] * t[1] * t[2] * 64; };
     auto maxlen_of = [&](int l) { double v = (double)base_cap * pow(4.0, (double)l); return (uint32_t)std::min<double>(std::min<double>(v, (double)n), 4.0e9); };
@@ -430,6 +464,7 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         a.c_hdr = c_hdr.p; a.c_ids = fin ? nullptr : c_ids.p; a.c_ent = fin ? ent.p : nullptr;
         a.pool_cursor = ctrl.p; a.pool_cap = cap; a.work_cursor = ctrl.p + 1; a.stats = ctrl.p + 2;
         a.maxlen = maxlen_of(l);
+        a.band = (float)band;
         if (is_top) {
             PCREG_REQUIRE(!fin, "vox_build: the top level cannot be the finest one");
             k_vox_top<<<(unsigned)slots_of(ld[l]), 256, 0, st>>>(a);
@@ -448,6 +483,7 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         if (fin) {
             m->v_listed = (int64_t)h_ctrl[2]; m->v_entries = (int64_t)h_ctrl[3];
             m->v_too_long = (int64_t)h_ctrl[4]; m->v_no_room = (int64_t)h_ctrl[5]; m->v_max_len = (int64_t)h_ctrl[6];
+            m->v_far = (int64_t)h_ctrl[7]; m->v_band = band;
             m->v_voxels = (int64_t)nvox_l;
         }
         p_hdr = std::move(c_hdr);
@@ -480,12 +516,12 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
 
 using namespace pcreg;
 
-extern "C" int pcreg_model_voxel_info(const pcreg_model* m, int32_t dims[3], double* voxel_size, int64_t stats[8]) {
+extern "C" int pcreg_model_voxel_info(const pcreg_model* m, int32_t dims[3], double* voxel_size, int64_t stats[10]) {
     if (!m) { set_error("pcreg_model_voxel_info: null model"); return PCREG_ERR_ARG; }
     if (!m->has_vox) {
         if (dims) dims[0] = dims[1] = dims[2] = 0;
         if (voxel_size) *voxel_size = 0.0;
-        if (stats) for (int k = 0; k < 8; ++k) stats[k] = 0;
+        if (stats) for (int k = 0; k < 10; ++k) stats[k] = 0;
         return PCREG_OK;
     }
     if (dims) for (int k = 0; k < 3; ++k) dims[k] = m->vox.dims[k];
@@ -494,6 +530,7 @@ extern "C" int pcreg_model_voxel_info(const pcreg_model* m, int32_t dims[3], dou
         stats[0] = m->v_voxels; stats[1] = m->v_listed; stats[2] = m->v_entries; stats[3] = m->v_too_long;
         stats[4] = m->v_no_room; stats[5] = m->v_max_len; stats[6] = (int64_t)(m->v_build_ms * 1000.0);
         stats[7] = (int64_t)(m->v_ent.bytes() + m->v_hdr.bytes());
+        stats[8] = m->v_far; stats[9] = (int64_t)(m->v_band * 1.0e6);
     }
     return PCREG_OK;
 }

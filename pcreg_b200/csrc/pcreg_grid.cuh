@@ -51,7 +51,7 @@ struct FusedArgs {
     unsigned long long* counters;           // profiling (may be null): [4] queries walked, [6] list entries read, [7] points gathered
 };
 size_t icp_fused_smem(int64_t ns, int mode);
-bool icp_fused_eligible(const pcreg_model* m, int64_t ns, const pcreg_icp_opts& o);
+bool icp_fused_eligible(const pcreg_model* m, int64_t ns, int64_t nhyp, const pcreg_icp_opts& o);
 void icp_fused_launch(FusedArgs& a, int64_t nhyp, cudaStream_t st);
 
 __device__ __forceinline__ void flush_counters(unsigned long long* counters, unsigned long long n_pts,

@@ -193,6 +193,8 @@ struct pcreg_model {
     pcreg::DevBuf<uint2> v_hdr;
     int64_t v_voxels = 0, v_listed = 0, v_entries = 0, v_too_long = 0, v_no_room = 0, v_max_len = 0;
     double v_build_ms = 0.0;
+    int64_t v_far = 0;          // voxels outside the band (band-limited map)
+    double v_band = 0.0;
 };
 
 namespace pcreg {

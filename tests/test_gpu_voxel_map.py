@@ -131,6 +131,7 @@ def test_fused_kernel_equals_per_pass_kernels_and_brute_force(pcreg, monkeypatch
           "knn-reject": dict(mode=pcreg.ICP_KNN, thDist2=9.0, k_frac=0.7),
           "weighted": dict(mode=pcreg.ICP_WEIGHTED, R_w=3.5, w_src=g.uniform(0.5, 1.0, src.shape[0]))}[mode]
     m = pcreg.Model(model, grid=True)
+    monkeypatch.setenv("PCREG_FUSED", "1")                 # (by default only batches of >= one hypothesis per SM run fused)
     pcreg.set_profiling(True)
     a = pcreg.icp_batch(m, src, T0, iters=14, nn=pcreg.NN_GRID, return_idx=True, return_hist=True, **kw)
     prof = pcreg.last_profile()
@@ -155,6 +156,7 @@ def test_fused_kernel_walks_queries_without_a_list(pcreg, monkeypatch):
     monkeypatch.setenv("PCREG_VOX_CAP", "8")
     m = pcreg.Model(model, grid=True, voxel_map=1, voxel_margin=-1.0)
     monkeypatch.delenv("PCREG_VOX_CAP")
+    monkeypatch.setenv("PCREG_FUSED", "1")
     pcreg.set_profiling(True)
     a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=10, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
     prof = pcreg.last_profile()
@@ -166,8 +168,9 @@ def test_fused_kernel_walks_queries_without_a_list(pcreg, monkeypatch):
     m.destroy()
 
 
-def test_fused_kernel_frozen_and_short_sources(pcreg):
+def test_fused_kernel_frozen_and_short_sources(pcreg, monkeypatch):
     """Fewer than 3 usable correspondences freezes the pose (status 1); tiny sources (ns < block size, ns = 1)."""
+    monkeypatch.setenv("PCREG_FUSED", "1")
     model = synth.make_model(20_000, 300)
     for ns in (1, 2, 37, 600):
         src, T_gt, c = synth.make_source(model, max(ns, 4), 0.3, 301)
@@ -180,3 +183,37 @@ def test_fused_kernel_frozen_and_short_sources(pcreg):
             for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
                 assert np.array_equal(a[k], r[k], equal_nan=True) if a[k].dtype.kind == "f" else np.array_equal(a[k], r[k]), (ns, kw, k)
         m.destroy()
+
+
+def test_fused_kernel_is_the_default_for_batches_that_fill_the_gpu(pcreg):
+    """>= one hypothesis per SM: the fused kernel runs by itself (no environment switch) and equals brute force."""
+    model = synth.make_model(40_000, 61)
+    src, T_gt, c = synth.make_source(model, 600, 0.3, 62)
+    T0 = synth.pose_grid(T_gt, c, 4, (4, 4, 3), 10.0, 1.5, 3)              # 192 hypotheses
+    m = pcreg.Model(model, grid=True)
+    pcreg.set_profiling(True)
+    a = pcreg.icp_batch(m, src, T0, mode=pcreg.ICP_KNN, iters=8, nn=pcreg.NN_GRID, return_idx=True, return_hist=True)
+    prof = pcreg.last_profile()
+    pcreg.set_profiling(False)
+    assert prof["fused"] == 1, prof
+    r = pcreg.icp_batch(m, src, T0[:24], mode=pcreg.ICP_KNN, iters=8, nn=pcreg.NN_BRUTE, return_idx=True, return_hist=True)
+    for k in ("T", "idx", "rmse", "rmse_hist", "n_used", "status"):
+        assert np.array_equal(a[k][:24], r[k]), k
+    m.destroy()
+
+
+def test_band_limited_map_of_dense_models(pcreg, monkeypatch):
+    """Dense models get lists only for the voxels within a band around the model (nn_vox.cu); queries beyond the band are
+    walked.  Forced here on a small model: results stay exact on both sides of the band."""
+    model = synth.make_model(60_000, 71)
+    g = synth.rng(72)
+    near = np.asarray(model[:3000], dtype=np.float64) + g.normal(0, 0.4, (3000, 3))
+    far = np.asarray(model[:1500], dtype=np.float64) + g.normal(0, 6.0, (1500, 3))
+    monkeypatch.setenv("PCREG_VOX_BAND", "1.5")
+    m = pcreg.Model(model, grid=True, voxel_map=1)
+    monkeypatch.delenv("PCREG_VOX_BAND")
+    info = m.voxel_info()
+    assert info["outside_band"] > 0 and abs(info["band"] - 1.5) < 1e-6 and info["listed"] > 0, info
+    prof = _nn_equal(pcreg, m, model, np.vstack([near, far]))
+    assert prof["certified_queries"] > 2000 and prof["walked_queries"] > 500, prof
+    m.destroy()
