@@ -29,6 +29,8 @@
 #include <math.h>
 #include <float.h>
 #include <stdlib.h>
+#include <stdio.h>
+#include <time.h>
 #include <algorithm>
 #include <array>
 #include <vector>
@@ -102,8 +104,11 @@ __device__ __forceinline__ void load_pivots(const GridPoint* __restrict__ pts, c
     }
 }
 
-// ---- top level: one BLOCK per voxel, lists filtered out of all points (streamed, coalesced) ------------------------------
-__global__ void __launch_bounds__(256) k_vox_top(const __grid_constant__ VoxLevelArgs a) {
+// ---- coarse levels: one BLOCK per voxel ----------------------------------------------------------------------------------
+// Candidates = ALL points (top level, HAS_PARENT = false: streamed, coalesced) or the parent's list (levels whose lists are
+// still thousands of points long: a warp per parent would take seconds there).
+template <bool HAS_PARENT>
+__global__ void __launch_bounds__(256) k_vox_block(const __grid_constant__ VoxLevelArgs a) {
     __shared__ unsigned long long s_best[8][9];
     __shared__ unsigned long long s_piv[9];
     __shared__ unsigned int s_cnt, s_off, s_ok;
@@ -111,6 +116,22 @@ __global__ void __launch_bounds__(256) k_vox_top(const __grid_constant__ VoxLeve
     int cx, cy, cz;
     brick_decode((int64_t)blockIdx.x, a.ct, cx, cy, cz);
     if (cx >= a.cd[0] || cy >= a.cd[1] || cz >= a.cd[2]) return;            // padding slot of the brick layout
+    const int64_t ci = brick_index(cx, cy, cz, a.ct);
+    uint32_t n_c = a.npts;
+    const int32_t* __restrict__ ids = nullptr;
+    if (HAS_PARENT) {
+        const uint2 ph = a.p_hdr[brick_index(cx >> 1, cy >> 1, cz >> 1, a.pt)];
+        if (ph.y == VOX_DROPPED || ph.y == 0u) {                            // block-uniform
+            if (tid == 0) a.c_hdr[ci] = make_uint2(0u, VOX_DROPPED);
+            return;
+        }
+        n_c = ph.y;
+        ids = a.p_ids + ph.x;
+    }
+    auto cand = [&](uint32_t t, uint32_t& id, double& x, double& y, double& z) {
+        id = HAS_PARENT ? (uint32_t)ids[t] : t;
+        x = a.pts[id].x; y = a.pts[id].y; z = a.pts[id].z;
+    };
     const double ccx = vox_centre(a.origin[0], cx, a.cs), ccy = vox_centre(a.origin[1], cy, a.cs), ccz = vox_centre(a.origin[2], cz, a.cs);
     const float e = (float)(0.5 * a.cs * (1.0 + 1e-4));
     const float tol_abs = 1e-6f * e * e;
@@ -118,9 +139,10 @@ __global__ void __launch_bounds__(256) k_vox_top(const __grid_constant__ VoxLeve
     unsigned long long best[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) best[j] = ~0ull;
-    for (uint32_t t = tid; t < a.npts; t += 256) {
-        const double px = a.pts[t].x, py = a.pts[t].y, pz = a.pts[t].z;
-        pivot_update(__double2float_rn(px - ccx), __double2float_rn(py - ccy), __double2float_rn(pz - ccz), e, t, best);
+    for (uint32_t t = tid; t < n_c; t += 256) {
+        uint32_t id; double px, py, pz;
+        cand(t, id, px, py, pz);
+        pivot_update(__double2float_rn(px - ccx), __double2float_rn(py - ccy), __double2float_rn(pz - ccz), e, id, best);
     }
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -143,22 +165,22 @@ __global__ void __launch_bounds__(256) k_vox_top(const __grid_constant__ VoxLeve
     // pivot 0 is the model point nearest to the voxel centre: a voxel that lies wholly farther than `band` from the model is
     // left without a list (its queries are walked) -- block-uniform
     if (a.band > 0.f && sqrtf(pv.n[0]) - 1.7320509f * e > a.band) {
-        if (tid == 0) { a.c_hdr[brick_index(cx, cy, cz, a.ct)] = make_uint2(0u, VOX_DROPPED); atomicAdd(&a.stats[5], 1ull); }
+        if (tid == 0) { a.c_hdr[ci] = make_uint2(0u, VOX_DROPPED); atomicAdd(&a.stats[5], 1ull); }
         return;
     }
     // pass 2: count
     unsigned int cnt = 0;
-    for (uint32_t t = tid; t < a.npts; t += 256) {
-        const double px = a.pts[t].x, py = a.pts[t].y, pz = a.pts[t].z;
+    for (uint32_t t = tid; t < n_c; t += 256) {
+        uint32_t id; double px, py, pz;
+        cand(t, id, px, py, pz);
         cnt += vox_keep(__double2float_rn(px - ccx), __double2float_rn(py - ccy), __double2float_rn(pz - ccz), pv, 2.f * e, tol_abs) ? 1u : 0u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
     __syncthreads();
-    const unsigned int total = s_cnt;
-    const int64_t ci = brick_index(cx, cy, cz, a.ct);
     if (tid == 0) {
+        const unsigned int total = s_cnt;
         if (total > a.maxlen) {
             a.c_hdr[ci] = make_uint2(0u, VOX_DROPPED);
             atomicAdd(&a.stats[2], 1ull);
@@ -179,11 +201,13 @@ __global__ void __launch_bounds__(256) k_vox_top(const __grid_constant__ VoxLeve
     if (!s_ok) return;
     // pass 3: write (order within the list is irrelevant)
     const unsigned int off = s_off;
-    for (uint32_t t0 = 0; t0 < a.npts; t0 += 256) {
+    for (uint32_t t0 = 0; t0 < n_c; t0 += 256) {
         const uint32_t t = t0 + tid;
         bool keep = false;
-        if (t < a.npts) {
-            const double px = a.pts[t].x, py = a.pts[t].y, pz = a.pts[t].z;
+        uint32_t id = 0;
+        if (t < n_c) {
+            double px, py, pz;
+            cand(t, id, px, py, pz);
             keep = vox_keep(__double2float_rn(px - ccx), __double2float_rn(py - ccy), __double2float_rn(pz - ccz), pv, 2.f * e, tol_abs);
         }
         const unsigned bm = __ballot_sync(0xffffffffu, keep);
@@ -191,7 +215,7 @@ __global__ void __launch_bounds__(256) k_vox_top(const __grid_constant__ VoxLeve
             unsigned int base = 0;
             if (lane == 0) base = atomicAdd(&s_cnt, (unsigned)__popc(bm));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) a.c_ids[off + base + __popc(bm & ((1u << lane) - 1u))] = (int32_t)t;
+            if (keep) a.c_ids[off + base + __popc(bm & ((1u << lane) - 1u))] = (int32_t)id;
         }
     }
 }
@@ -388,7 +412,7 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
     double s = scale * delta;
     if (!(s > 0.0) || !std::isfinite(s)) return;
     const double margin = o.voxel_margin > 0.0 ? o.voxel_margin : (o.voxel_margin < 0.0 ? 0.0 : env_double("PCREG_VOX_MARGIN", 0.04) * maxext);
-    const size_t budget_bytes = c.total_mem / 8;                      // entries of the finest level
+    size_t budget_bytes = c.total_mem / 8;                            // entries of the finest level (band-limited maps: 1/5 of the memory)
     const double max_vox = (double)(o.max_voxels > 0 ? o.max_voxels : std::min<int64_t>((int64_t)1 << 27, (int64_t)(budget_bytes / 128)));
     int32_t dims[3];
     auto size_for = [&](double edge) {
@@ -409,10 +433,12 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         double nvb = size_for(sb);
         while (nvb > hdr_budget && sb < 6.0 * delta) { sb *= 1.05; nvb = size_for(sb); }
         const double area = occ * cell * cell;
-        const double b = max_vox * sb * sb * sb / (2.0 * area);                 // slab of +- band around the surface holds ~max_vox voxels
+        const double max_near = env_double("PCREG_VOX_NEAR", 268435456.0);       // listed voxels (2^28: C5 -> band ~6 mm, ~15 GB)
+        const double b = max_near * sb * sb * sb / (2.0 * area);                // slab of +- band around the surface holds ~max_near voxels
         if (nvb <= hdr_budget && b >= 4.0 * sb) {
             s = sb; nv = nvb; band = std::min(b, maxext);
             base_cap = std::max(base_cap, 192);
+            budget_bytes = c.total_mem / 5;
         }
     }
     if (band == 0.0 && env_double("PCREG_VOX_BAND", 0.0) > 0.0) band = env_double("PCREG_VOX_BAND", 0.0);      // tests: force a band
@@ -423,7 +449,9 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
     }
     std::vector<std::array<int32_t, 3>> ld;
     ld.push_back({dims[0], dims[1], dims[2]});
-    while (std::max({ld.back()[0], ld.back()[1], ld.back()[2]}) > VOX_TOP_DIM)
+    // the top level filters ALL points per voxel (cost: voxels x points): fewer, larger top voxels for large models
+    const int top_dim = n > 2000000 ? VOX_TOP_DIM / 2 : VOX_TOP_DIM;
+    while (std::max({ld.back()[0], ld.back()[1], ld.back()[2]}) > top_dim)
         ld.push_back({(ld.back()[0] + 1) / 2, (ld.back()[1] + 1) / 2, (ld.back()[2] + 1) / 2});
     const int top = (int)ld.size() - 1;
     if (top == 0) {                                                   // tiny map: give the top-level kernel a level of its own
@@ -438,10 +466,13 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
     auto slots_of = [&](const std::array<int32_t, 3>& d) { int32_t t[3]; tiles_of(d, t); return (size_t)t[0] * t[1] * t[2] * 64; };
     auto maxlen_of = [&](int l) { double v = (double)base_cap * pow(4.0, (double)l); return (uint32_t)std::min<double>(std::min<double>(v, (double)n), 4.0e9); };
 
+    static const bool dbg = [] { const char* e = getenv("PCREG_DEBUG_HOST"); return e && e[0] == '1'; }();
+    auto dbg_now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec; };
+    double t_level = dbg ? (cudaStreamSynchronize(st), dbg_now()) : 0.0;
     DevBuf<uint2> p_hdr, c_hdr;
     DevBuf<int32_t> p_ids, c_ids;
     DevBuf<float4> ent;
-    unsigned long long used = 0, h_ctrl[8];
+    unsigned long long used = 0, listed_parent = 0, h_ctrl[8];
     const double origin[3] = {m->bbox_lo[0] - margin, m->bbox_lo[1] - margin, m->bbox_lo[2] - margin};
     for (int l = L - 1; l >= 0; --l) {
         const bool is_top = (l == L - 1), fin = (l == 0);
@@ -465,13 +496,18 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         a.pool_cursor = ctrl.p; a.pool_cap = cap; a.work_cursor = ctrl.p + 1; a.stats = ctrl.p + 2;
         a.maxlen = maxlen_of(l);
         a.band = (float)band;
-        if (is_top) {
-            PCREG_REQUIRE(!fin, "vox_build: the top level cannot be the finest one");
-            k_vox_top<<<(unsigned)slots_of(ld[l]), 256, 0, st>>>(a);
-        } else {
+        if (!is_top) {
             a.p_hdr = p_hdr.p; a.p_ids = p_ids.p;
             for (int k = 0; k < 3; ++k) a.pd[k] = ld[l + 1][k];
             tiles_of(ld[l + 1], a.pt);
+        }
+        if (is_top) {
+            PCREG_REQUIRE(!fin, "vox_build: the top level cannot be the finest one");
+            k_vox_block<false><<<(unsigned)slots_of(ld[l]), 256, 0, st>>>(a);
+        } else if (!fin && listed_parent > 0 && used / listed_parent > 768 && slots_of(ld[l]) < ((size_t)1 << 22)) {
+            // long parent lists (coarse levels): a block per child voxel
+            k_vox_block<true><<<(unsigned)slots_of(ld[l]), 256, 0, st>>>(a);
+        } else {
             const int blocks = (int)std::min<size_t>((slots_of(ld[l + 1]) + 255) / 256 + 1, (size_t)c.sm_count * 8);
             if (fin) k_vox_refine<true><<<blocks, 256, 0, st>>>(a);
             else     k_vox_refine<false><<<blocks, 256, 0, st>>>(a);
@@ -480,6 +516,13 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         PCREG_CUDA(cudaMemcpyAsync(h_ctrl, ctrl.p, sizeof h_ctrl, cudaMemcpyDeviceToHost, st));
         PCREG_CUDA(cudaStreamSynchronize(st));
         used = std::min<unsigned long long>(h_ctrl[0], cap);
+        listed_parent = h_ctrl[2];
+        if (dbg) {
+            const double t = dbg_now();
+            fprintf(stderr, "[pcreg vox] level %d (%d x %d x %d, edge %.4g): %.1f ms, %llu listed, %llu entries, %llu too long, %llu no room, %llu far, longest %llu\n",
+                    l, ld[l][0], ld[l][1], ld[l][2], a.cs, t - t_level, h_ctrl[2], h_ctrl[3], h_ctrl[4], h_ctrl[5], h_ctrl[7], h_ctrl[6]);
+            t_level = t;
+        }
         if (fin) {
             m->v_listed = (int64_t)h_ctrl[2]; m->v_entries = (int64_t)h_ctrl[3];
             m->v_too_long = (int64_t)h_ctrl[4]; m->v_no_room = (int64_t)h_ctrl[5]; m->v_max_len = (int64_t)h_ctrl[6];
