@@ -433,7 +433,7 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         double nvb = size_for(sb);
         while (nvb > hdr_budget && sb < 6.0 * delta) { sb *= 1.05; nvb = size_for(sb); }
         const double area = occ * cell * cell;
-        const double max_near = env_double("PCREG_VOX_NEAR", 268435456.0);       // listed voxels (2^28: C5 -> band ~6 mm, ~15 GB)
+        const double max_near = env_double("PCREG_VOX_NEAR", 536870912.0);       // listed voxels (2^29: C5 -> band ~12 mm)
         const double b = max_near * sb * sb * sb / (2.0 * area);                // slab of +- band around the surface holds ~max_near voxels
         if (nvb <= hdr_budget && b >= 4.0 * sb) {
             s = sb; nv = nvb; band = std::min(b, maxext);
