@@ -93,6 +93,14 @@ int  pcreg_model_voxel_info(const pcreg_model* m, int32_t dims[3], double* voxel
 int  pcreg_nn_search(const pcreg_model* m, const void* q, int is_double, int64_t nq, int64_t ld,
                      int nn_kind, int32_t* idx /*[nq]*/, double* d2 /*[nq] squared distance, may be NULL*/);
 
+/* ---- pose application to a whole cloud: quickTF.m:1-8, invertTF.m:1-8, AutoAlignPointclouds.m:8 ------------ */
+#define PCREG_TF_FORWARD   0   /* [p 1] * T                          (quickTF.m:5-7)                                      */
+#define PCREG_TF_INVERT    1   /* [p 1] * invertTF(T) = [R' 0; -t R' 1]  (quickTF(pts, invertTF(T)), AutoAlignPointclouds2.m:25) */
+#define PCREG_TF_MRDIVIDE  2   /* [p 1] / T, the general 4x4 inverse  (AutoAlignPointclouds.m:8)                           */
+/* pts: n x 3 column-major (ld), class single or double; out: the same class and shape (ld_out).  The last step of the
+ * reference path on the full model cloud (16 M points in C5). */
+int  pcreg_quick_tf(const void* pts, int is_double, int64_t n, int64_t ld, const double* T16, int mode, void* out, int64_t ld_out);
+
 /* ---- getLocalPoints.m:5-36, batched over centres ------------------------------------------------ */
 /* For each centre c_k (nc x 3 column-major doubles, ld): the model points with vecnorm(p - c_k) < R
  * (strict), RELATIVE to c_k, in ORIGINAL model order, class double.  Two calls:

@@ -64,6 +64,7 @@ SIGNATURES = {
     "pcreg_model_size": (C.c_int64, [C.c_void_p]),
     "pcreg_model_grid_info": (C.c_int, [C.c_void_p, c_i32p, c_f64p, c_i64p]),
     "pcreg_model_voxel_info": (C.c_int, [C.c_void_p, c_i32p, c_f64p, c_i64p]),
+    "pcreg_quick_tf": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, c_f64p, C.c_int, C.c_void_p, C.c_int64]),
     "pcreg_nn_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, c_i32p, c_f64p]),
     "pcreg_local_points_count": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, c_i64p, c_i32p]),
     "pcreg_local_points_fill": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.c_double, c_i64p, c_i32p, c_f64p, C.c_int64,

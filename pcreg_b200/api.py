@@ -114,6 +114,23 @@ class Model:
 
 
 # ------------------------------------------------------------------------------------------------
+# pose application (quickTF.m, invertTF.m, AutoAlignPointclouds.m:8)
+# ------------------------------------------------------------------------------------------------
+TF_FORWARD, TF_INVERT, TF_MRDIVIDE = 0, 1, 2
+
+
+def quickTF(pts, TF, mode: int = TF_FORWARD):
+    """quickTF.m:1-8 on the GPU: [pts 1] * TF (class of pts kept).  mode=TF_INVERT applies invertTF(TF) (invertTF.m:5-7, as
+    AutoAlignPointclouds2.m:25 does), mode=TF_MRDIVIDE computes [pts 1] / TF (AutoAlignPointclouds.m:8)."""
+    a, is_double, n = _cm_points(pts)
+    out = np.empty_like(a, order="F")
+    T = _T_to_abi(np.asarray(TF, dtype=np.float64).reshape(4, 4))
+    L.check(L.lib().pcreg_quick_tf(a.ctypes.data_as(C.c_void_p), is_double, n, n, _ptr(T, L.c_f64p), int(mode),
+                                   out.ctypes.data_as(C.c_void_p), n), "pcreg_quick_tf")
+    return np.ascontiguousarray(out)
+
+
+# ------------------------------------------------------------------------------------------------
 # getLocalPoints
 # ------------------------------------------------------------------------------------------------
 def getLocalPoints_batch(model: Model, centres, R, min_points, max_points, return_idx=False):

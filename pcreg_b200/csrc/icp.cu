@@ -28,8 +28,10 @@
 
 namespace pcreg {
 
+struct Pose16 { double t[16]; };      // a row-major row-vector pose as a kernel argument
+
 // One block per hypothesis.
-__global__ void __launch_bounds__(UPD_THREADS, 1) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
+__global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
     __shared__ double Ts[16];
     __shared__ double red[KABSCH_NSUMS * 32];
     __shared__ long long redll[32];
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_icp_update(const __grid_cons
         if (a.update && !a.frozen[h]) {
             double Tn[16], Tc[16];
             for (int k = 0; k < 16; ++k) Tc[k] = Ts[k];
-            if (!icp_pose_update(s, n_used, a.pivot, a.reflection_fix != 0, Tc, Tn)) {
+            if (!icp_pose_update_call(s, n_used, a.pivot, a.reflection_fix != 0, Tc, Tn)) {
                 a.frozen[h] = 1;
             } else {
                 for (int k = 0; k < 16; ++k) a.T[h * 16 + k] = Tn[k];
@@ -335,6 +337,16 @@ __global__ void k_transpose16(const double* __restrict__ in, double* __restrict_
     const int64_t h = g >> 4;
     const int e = (int)(g & 15), r = e >> 2, c = e & 3;
     out[h * 16 + r * 4 + c] = in[h * 16 + c * 4 + r];
+}
+
+// [p 1] * T for a whole cloud (quickTF.m:5-7), T row-major in constant arguments; class of the input kept
+template <typename F>
+__global__ void k_quick_tf(const F* __restrict__ in, int64_t n, int64_t ld_in, F* __restrict__ out, int64_t ld_out, const __grid_constant__ Pose16 T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double qx, qy, qz;
+    quick_tf(T.t, (double)in[i], (double)in[ld_in + i], (double)in[2 * ld_in + i], qx, qy, qz);
+    out[i] = (F)qx; out[ld_out + i] = (F)qy; out[2 * ld_out + i] = (F)qz;
 }
 
 void transpose16_launch(const double* d_in, double* d_out, int64_t n, cudaStream_t st) {
@@ -730,6 +742,53 @@ int pcreg_icp_batch(const pcreg_model* m, const void* src, int is_double, int64_
         for (int64_t h = 0; h < nhyp; ++h) if (rm[h] == rm[h] && (bi < 0 || rm[h] < rm[bi])) bi = h;
         *best = bi;
     }
+    return PCREG_OK;
+    PCREG_API_END
+}
+
+int pcreg_quick_tf(const void* pts, int is_double, int64_t n, int64_t ld, const double* T16, int mode, void* out, int64_t ld_out) {
+    PCREG_API_BEGIN
+    require_init();
+    PCREG_REQUIRE(pts && T16 && out, "pcreg_quick_tf: null pointer");
+    PCREG_REQUIRE(n >= 1 && ld >= n && ld_out >= n, "pcreg_quick_tf: bad sizes");
+    PCREG_REQUIRE(mode >= PCREG_TF_FORWARD && mode <= PCREG_TF_MRDIVIDE, "pcreg_quick_tf: bad mode");
+    // math layout M[r][c] from the column-major record
+    double M[4][4];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M[r][c] = T16[c * 4 + r];
+    Pose16 P{};
+    if (mode == PCREG_TF_FORWARD) {
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) P.t[r * 4 + c] = M[r][c];
+    } else if (mode == PCREG_TF_INVERT) {               // invertTF.m:5-7: [R' 0; -t R' 1]
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) P.t[r * 4 + c] = M[c][r];
+        for (int c = 0; c < 3; ++c) P.t[12 + c] = -(M[3][0] * M[c][0] + M[3][1] * M[c][1] + M[3][2] * M[c][2]);
+        P.t[3] = P.t[7] = P.t[11] = 0.0; P.t[15] = 1.0;
+    } else {                                            // [p 1] / T: the general inverse (AutoAlignPointclouds.m:8), Gauss-Jordan with pivoting
+        double A[4][8];
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { A[r][c] = M[r][c]; A[r][4 + c] = r == c ? 1.0 : 0.0; }
+        for (int k = 0; k < 4; ++k) {
+            int piv = k;
+            for (int r = k + 1; r < 4; ++r) if (fabs(A[r][k]) > fabs(A[piv][k])) piv = r;
+            PCREG_REQUIRE(A[piv][k] != 0.0, "pcreg_quick_tf: singular transform");
+            if (piv != k) for (int c = 0; c < 8; ++c) std::swap(A[k][c], A[piv][c]);
+            const double d = A[k][k];
+            for (int c = 0; c < 8; ++c) A[k][c] /= d;
+            for (int r = 0; r < 4; ++r) if (r != k) { const double f = A[r][k]; for (int c = 0; c < 8; ++c) A[r][c] -= f * A[k][c]; }
+        }
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) P.t[r * 4 + c] = A[r][4 + c];
+    }
+    PCREG_CUDA(cudaSetDevice(ctx().device));
+    cudaStream_t st = 0;
+    const size_t el = is_double ? 8 : 4;
+    DevBuf<unsigned char> d_in((size_t)n * 3 * el), d_out((size_t)n * 3 * el);
+    for (int a = 0; a < 3; ++a)
+        PCREG_CUDA(cudaMemcpyAsync(d_in.p + (size_t)a * n * el, (const unsigned char*)pts + (size_t)a * ld * el, (size_t)n * el, cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (is_double) k_quick_tf<double><<<blocks, 256, 0, st>>>((const double*)d_in.p, n, n, (double*)d_out.p, n, P);
+    else           k_quick_tf<float><<<blocks, 256, 0, st>>>((const float*)d_in.p, n, n, (float*)d_out.p, n, P);
+    PCREG_LAUNCHED();
+    for (int a = 0; a < 3; ++a)
+        PCREG_CUDA(cudaMemcpyAsync((unsigned char*)out + (size_t)a * ld_out * el, d_out.p + (size_t)a * n * el, (size_t)n * el, cudaMemcpyDeviceToHost, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));
     return PCREG_OK;
     PCREG_API_END
 }

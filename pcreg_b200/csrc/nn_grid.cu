@@ -506,7 +506,6 @@ __global__ void __launch_bounds__(128) k_nn_grid_walk(const __grid_constant__ Gr
     const bool chained = (a.worklist == nullptr);
     const int64_t count = chained ? (a.nq + a.chain - 1) / a.chain : (int64_t)*a.work_count;
     if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters[4], (unsigned long long)(chained ? a.nq : count));
-    const double inv_cell2 = G.inv_cell * G.inv_cell;
     unsigned long long n_pts = 0, n_cells = 0, n_nodes = 0;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < count; w += (int64_t)gridDim.x * blockDim.x) {
         const int nchain = chained ? (int)min((int64_t)a.chain, a.nq - w * a.chain) : 1;

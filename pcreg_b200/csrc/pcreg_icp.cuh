@@ -53,4 +53,10 @@ __device__ __forceinline__ bool icp_pose_update(const double (&s)[KABSCH_NSUMS],
     return true;
 }
 
+// out-of-line copy for the kernels' hot loops' sake: one thread per hypothesis runs it, its SVD must not claim their registers
+__device__ __noinline__ static bool icp_pose_update_call(const double (&s)[KABSCH_NSUMS], long long n_used, const double* pivot,
+                                                         bool reflection_fix, const double* Tc, double* Tn) {
+    return icp_pose_update(s, n_used, pivot, reflection_fix, Tc, Tn);
+}
+
 }  // namespace pcreg

@@ -7,6 +7,7 @@
 #include <vector>
 #include <memory>
 #include <new>
+#include <exception>
 
 #include "../../include/pcreg.h"
 
@@ -111,7 +112,15 @@ struct DevBuf {
         if (count == 0) return;
         p = (T*)pool_alloc(count * sizeof(T));
     }
-    void release() { if (p) pool_free(p); p = nullptr; n = 0; }
+    // On an error path (stack unwinding) kernels queued before the throw may still use the buffer: drain the device before
+    // the block goes back to the pool, so that the next call cannot be handed memory that is still being written.
+    void release() {
+        if (p) {
+            if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
+            pool_free(p);
+        }
+        p = nullptr; n = 0;
+    }
     size_t bytes() const { return n * sizeof(T); }
 };
 

@@ -105,6 +105,20 @@ bool cmd_nn_search(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     return true;
 }
 
+// pts_tf = pcreg_mex('quick_tf', pts, TF[, mode])   mode 0: [pts 1]*TF (quickTF.m), 1: [pts 1]*invertTF(TF), 2: [pts 1]/TF
+bool cmd_quick_tf(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 3 || !is_pts(prhs[1]) || !mxIsDouble(prhs[2]) || mxGetM(prhs[2]) != 4 || mxGetN(prhs[2]) != 4) {
+        g_fail = "quick_tf: need (pts Nx3 single or double, TF 4x4 double[, mode])"; return false;
+    }
+    const int64_t n = (int64_t)mxGetM(prhs[1]);
+    const int mode = nrhs > 3 ? (int)mxGetScalar(prhs[3]) : PCREG_TF_FORWARD;
+    if (n == 0) { plhs[0] = mxCreateNumericMatrix(0, 3, mxIsDouble(prhs[1]) ? mxDOUBLE_CLASS : mxSINGLE_CLASS, mxREAL); return true; }
+    plhs[0] = mxCreateNumericMatrix((mwSize)n, 3, mxIsDouble(prhs[1]) ? mxDOUBLE_CLASS : mxSINGLE_CLASS, mxREAL);
+    const int rc = pcreg_quick_tf(mxGetData(prhs[1]), mxIsDouble(prhs[1]), n, n, mxGetPr(prhs[2]), mode, mxGetData(plhs[0]), n);
+    if (rc != PCREG_OK) { g_fail = pcreg_last_error(); mxDestroyArray(plhs[0]); plhs[0] = nullptr; return false; }
+    return true;
+}
+
 bool cmd_local_points(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     pcreg_model* m = nrhs > 1 ? handle_of(prhs[1]) : nullptr;
     if (!m || nrhs < 6 || !is_pts(prhs[2]) || !mxIsDouble(prhs[2])) { g_fail = "local_points: need (handle, c Kx3 double, R, min_points, max_points)"; return false; }
@@ -420,6 +434,7 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
         } else if (!strcmp(cmd, "model_create")) ok = cmd_model_create(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "model_destroy")) { pcreg_model_destroy(nrhs > 1 ? handle_of(prhs[1]) : nullptr); ok = true; if (nlhs > 0) plhs[0] = empty(); }
         else if (!strcmp(cmd, "nn_search")) ok = cmd_nn_search(nlhs, plhs, nrhs, prhs);
+        else if (!strcmp(cmd, "quick_tf")) ok = cmd_quick_tf(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "local_points")) ok = cmd_local_points(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "spatial_histogram")) ok = cmd_spatial_histogram(nlhs, plhs, nrhs, prhs);
         else if (!strcmp(cmd, "align")) ok = cmd_align(nlhs, plhs, nrhs, prhs);

@@ -94,6 +94,7 @@ int mexAtExit(void (*fn)(void)) { g_atexit = fn; return 0; }
 // stubs of the C ABI: record the arguments, return canned results
 // ---------------------------------------------------------------------------------------------------------
 struct Rec {
+    int tf_mode = -1, tf_is_double = -1; int64_t tf_n = 0; double tf_t41 = 0.0;
     int init_dev = -1, init_ndev = 0, init_last = -1, inits = 0, shutdowns = 0;
     int model_is_double = -1; int64_t model_n = 0, model_ld = 0; int model_grid = -1;
     int nn_kind = -1; int64_t nn_nq = 0; int nn_is_double = -1;
@@ -122,6 +123,12 @@ int pcreg_model_create(const void*, int is_double, int64_t n, int64_t ld, const 
     return PCREG_OK;
 }
 int pcreg_model_destroy(pcreg_model* m) { R.destroyed = m; return PCREG_OK; }
+int pcreg_quick_tf(const void* pts, int is_double, int64_t n, int64_t ld, const double* T16, int mode, void* out, int64_t ld_out) {
+    MAYBE_FAIL();
+    R.tf_mode = mode; R.tf_n = n; R.tf_is_double = is_double; R.tf_t41 = T16[3];          // element (4,1) of the column-major record
+    if (is_double) for (int64_t i = 0; i < n; ++i) ((double*)out)[ld_out + i] = ((const double*)pts)[ld + i] + 100.0;   // y column + 100
+    return PCREG_OK;
+}
 int pcreg_nn_search(const pcreg_model* m, const void*, int is_double, int64_t nq, int64_t, int kind, int32_t* idx, double* d2) {
     MAYBE_FAIL();
     if (m != HANDLE) return PCREG_ERR_STATE;
@@ -297,6 +304,12 @@ int main() {
       CHECK(o.a[0]->m == 5 && o.a[0]->n == 1 && mxGetPr(o.a[0])[0] == 1.0 && mxGetPr(o.a[0])[4] == 5.0 && mxGetPr(o.a[1])[3] == 13.0); release(o); }
     { Out o = call(1, {str("nn_search"), handle, dbl(2, 3), str("grid")}); CHECK(R.nn_kind == PCREG_NN_GRID); release(o); }
     { Out o = call(1, {str("nn_search"), dbl(1, 1, {5}), dbl(2, 3)}); CHECK(!o.err.empty()); release(o); }          // not a uint64 handle
+
+    // ---- quick_tf: class kept, the 4x4 handed over as MATLAB stores it, mode optional ----
+    { Out o = call(1, {str("quick_tf"), dbl(3, 3, {1, 2, 3, 4, 5, 6, 7, 8, 9}), dbl(4, 4, {1, 0, 0, 13, 0, 1, 0, 25, 0, 0, 1, -17, 0, 0, 0, 1}), dbl(1, 1, {2})});
+      CHECK(o.err.empty() && R.tf_mode == PCREG_TF_MRDIVIDE && R.tf_n == 3 && R.tf_is_double == 1 && R.tf_t41 == 13.0);
+      CHECK(o.a[0]->m == 3 && o.a[0]->n == 3 && mxGetPr(o.a[0])[3] == 104.0); release(o); }
+    { Out o = call(1, {str("quick_tf"), dbl(3, 3), dbl(3, 3)}); CHECK(!o.err.empty()); release(o); }                    // TF must be 4 x 4
 
     // ---- estimate_transform: 4x4 column-major as the ABI wrote it; status 1 -> [] ----
     { R.kabsch_status = 0; Out o = call(1, {str("estimate_transform"), dbl(4, 3, {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12}), dbl(4, 3)});

@@ -234,3 +234,21 @@ def test_ransac_batch_reference_driver_shape(pcreg):
         want = oracle.ransac(p1s[w], p2s[w], coef, oracle.ransac_triplets(w, 20_000, p1s[w].shape[0]))
         assert got[w]["best"] == want["best"] and got[w]["numSuccess"] == want["numSuccess"]
         assert np.array_equal(got[w]["inlierIdx"], want["inlierIdx"])
+
+
+def test_quick_tf_on_a_whole_cloud(pcreg):
+    """quickTF.m:5-7, quickTF(pts, invertTF(T)) (AutoAlignPointclouds2.m:25) and [pts 1] / T (AutoAlignPointclouds.m:8) on the
+    device: forward bit-exact against the oracle's operation order, both inverse forms against numpy, class single kept."""
+    g = synth.rng(8)
+    pts = g.normal(0, 40, (200_003, 3))
+    T = synth.make_T(synth.rot_xyz([0.4, -1.1, 2.0]), np.array([13.0, 25.0, -17.0]))
+    fwd = pcreg.quickTF(pts, T)
+    assert np.array_equal(fwd, oracle.quickTF(pts, T))
+    inv = pcreg.quickTF(fwd, T, pcreg.TF_INVERT)
+    assert np.array_equal(inv, oracle.quickTF(fwd, oracle.invertTF(T)))
+    np.testing.assert_allclose(inv, pts, atol=1e-11)
+    div = pcreg.quickTF(fwd, T, pcreg.TF_MRDIVIDE)
+    np.testing.assert_allclose(div, (np.column_stack([fwd, np.ones(len(fwd))]) @ np.linalg.inv(T))[:, :3], atol=1e-10)
+    s = pcreg.quickTF(pts.astype(np.float32), T)
+    assert s.dtype == np.float32
+    np.testing.assert_allclose(s, fwd, rtol=1e-6, atol=1e-4)
