@@ -148,14 +148,18 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+# the sources of the kernels whose DRAM traffic profiles/roofline_traffic.json records
+TRAFFIC_SOURCES = ("icp.cu", "icp_fused.cu", "nn_brute.cu", "nn_grid.cu", "nn_vox.cu", "pcreg_dev.cuh", "pcreg_grid.cuh", "pcreg_icp.cuh",
+                   "pcreg_math.cuh", "pcreg_select.cuh", "pcreg_vox.cuh")
+
+
 def kernel_source_sha():
     """Hash of the CUDA sources: profiles/roofline_traffic.json is only used while it matches the code it was captured from."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "pcreg_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".h")):
-            with open(os.path.join(d, name), "rb") as f:
-                h.update(name.encode()); h.update(f.read())
+    for name in TRAFFIC_SOURCES:
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode()); h.update(f.read())
     return h.hexdigest()[:16]
 
 
