@@ -13,7 +13,7 @@ for rep in sys.argv[1:]:
     scale = lambda u: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
     acc = {}
     for r in rows[2:]:
-        k = r[ik].split("(")[0].split("<")[0]
+        k = r[ik].split("(")[0].split("<")[0].replace("void ", "").replace("pcreg::", "").strip()
         b = float(r[ir].replace(",", "")) * scale(units[ir]) + float(r[iw].replace(",", "")) * scale(units[iw])
         acc.setdefault(k, []).append(b)
     for k, v in acc.items():
