@@ -31,7 +31,10 @@ namespace pcreg {
 struct Pose16 { double t[16]; };      // a row-major row-vector pose as a kernel argument
 
 // One block per hypothesis.
-__global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
+// NT = threads per hypothesis: UPD_THREADS (the fused kernel's count, so that both sum in the same order and agree bit for
+// bit) for sources the fused kernel can take, 512 for large sources (C5: 65 536 correspondences per hypothesis).
+template <int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 3 : 1) k_icp_update(const __grid_constant__ IcpUpdateArgs a) {
     __shared__ double Ts[16];
     __shared__ double red[KABSCH_NSUMS * 32];
     __shared__ long long redll[32];
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_cons
         unsigned long long* __restrict__ keys = a.keys + h * ns;
         long long nkept = 0;
         unsigned long long kmin = ~0ull, kmax = 0ull;
-        for (int64_t i = tid; i < ns; i += UPD_THREADS) {
+        for (int64_t i = tid; i < ns; i += NT) {
             const double d = d2[i];
             const bool keep = idx[i] >= 0 && (!reject || d < a.thDist2);
             const unsigned long long key = keep ? dbits(__dsqrt_rn(d)) : KEY_NOSEL;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_cons
             if (lane == 0) { red_u64[warp] = kmin; red_u64[32 + warp] = kmax; }
             __syncthreads();
             kmin = ~0ull; kmax = 0ull;
-            for (int w = 0; w < UPD_THREADS / 32; ++w) {
+            for (int w = 0; w < NT / 32; ++w) {
                 kmin = red_u64[w] < kmin ? red_u64[w] : kmin;
                 kmax = red_u64[32 + w] > kmax ? red_u64[32 + w] : kmax;
             }
@@ -109,12 +112,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_cons
         return w;
     };
     constexpr int UB = 4;
-    for (int64_t i0 = tid; i0 < ns; i0 += (int64_t)UB * UPD_THREADS) {
+    for (int64_t i0 = tid; i0 < ns; i0 += (int64_t)UB * NT) {
         int32_t jj[UB]; double dd[UB], xs[UB], ys[UB], zs[UB], ww[UB];
         ModelPointD mm[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-            const int64_t i = i0 + (int64_t)u * UPD_THREADS;
+            const int64_t i = i0 + (int64_t)u * NT;
             const bool ok = i < ns;
             const int64_t ic = ok ? i : tid;                 // tid < ns is guaranteed inside the loop
             jj[u] = ok ? idx[ic] : -1;
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_icp_update(const __grid_cons
         for (int u = 0; u < UB; ++u) mm[u] = a.md[jj[u] >= 0 ? jj[u] : 0];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-            const int64_t i = i0 + (int64_t)u * UPD_THREADS;
+            const int64_t i = i0 + (int64_t)u * NT;
             ww[u] = (i < ns) ? weight_of(i, jj[u], dd[u]) : 0.0;
         }
 #pragma unroll
@@ -354,7 +357,8 @@ void transpose16_launch(const double* d_in, double* d_out, int64_t n, cudaStream
     PCREG_LAUNCHED();
 }
 void icp_update_launch(const IcpUpdateArgs& a, int64_t nhyp, cudaStream_t st) {
-    k_icp_update<<<(unsigned)nhyp, UPD_THREADS, 0, st>>>(a);
+    if (a.ns > 20000) k_icp_update<512><<<(unsigned)nhyp, 512, 0, st>>>(a);
+    else              k_icp_update<UPD_THREADS><<<(unsigned)nhyp, UPD_THREADS, 0, st>>>(a);
     PCREG_LAUNCHED();
 }
 void icp_argmin_launch(const double* d_rmse, int64_t nhyp, int64_t* d_best, cudaStream_t st) {

@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
             int32_t b0 = -1, b1 = -1;
             double d0 = INFINITY, d1 = INFINITY;
             unsigned ng = 0;
-            if (ok0) { vox_scan(V, pts, hd0, x0, y0, z0, q0x, q0y, q0z, b0, d0, ng); c_read += hd0.y; c_gather += ng; }
+            if (ok0) { vox_scan<8>(V, pts, hd0, x0, y0, z0, q0x, q0y, q0z, b0, d0, ng); c_read += hd0.y; c_gather += ng; }
             else     { fused_walk(a.g, q0x, q0y, q0z, it > 0 ? idx_s[i0] : -1, b0, d0); ++c_walk; }
             if (has1) {
-                if (ok1) { vox_scan(V, pts, hd1, x1, y1, z1, q1x, q1y, q1z, b1, d1, ng); c_read += hd1.y; c_gather += ng; }
+                if (ok1) { vox_scan<8>(V, pts, hd1, x1, y1, z1, q1x, q1y, q1z, b1, d1, ng); c_read += hd1.y; c_gather += ng; }
                 else     { fused_walk(a.g, q1x, q1y, q1z, it > 0 ? idx_s[i1] : -1, b1, d1); ++c_walk; }
             }
             idx_s[i0] = b0;
@@ -147,18 +147,22 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
 #pragma unroll
         for (int k = 0; k < KABSCH_NSUMS; ++k) s[k] = 0.0;
         long long n_used = 0;
-        for (int i = tid; i < ns; i += UPD_THREADS) {
-            const int32_t j = idx_s[i];
-            double qx, qy, qz;
-            quick_tf(Ts, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
-            const ModelPointD m = a.g.md[j >= 0 ? j : 0];
-            const double d = j >= 0 ? dist2_exact(m.x, m.y, m.z, qx, qy, qz) : (double)INFINITY;      // the NN step's d2, bit for bit
+        auto weight_of = [&](int i, int32_t j, double d) -> double {
             const bool keep = j >= 0 && (!reject || d < a.thDist2);
             double w = 0.0;
             if (a.mode == PCREG_ICP_PLAIN) w = keep ? 1.0 : 0.0;
             else if (knn) w = (j >= 0 && key_selected(keys_s[i], vK, all_eq)) ? 1.0 : 0.0;
             else if (keep) w = fmax(__dsub_rn(a.R_w, __dsqrt_rn(d)), 0.0);
             if (a.w_src) w = __dmul_rn(w, a.w_src[i]);
+            return w;
+        };
+        for (int i = tid; i < ns; i += UPD_THREADS) {
+            const int32_t j = idx_s[i];
+            double qx, qy, qz;
+            quick_tf(Ts, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
+            const ModelPointD m = a.g.md[j >= 0 ? j : 0];
+            const double d = j >= 0 ? dist2_exact(m.x, m.y, m.z, qx, qy, qz) : (double)INFINITY;      // the NN step's d2, bit for bit
+            const double w = weight_of(i, j, d);
             if (w > 0.0) ++n_used;
             icp_accumulate(s, w, d, qx, qy, qz, m, px, py, pz);
         }

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) k_nn_vox(const __grid_constant__ GridArgs
         float x, y, z;
         if (vox_lookup(V, qx, qy, qz, hd, x, y, z)) {
             int32_t bidx; double best; unsigned ng;
-            vox_scan(V, a.g.pts, hd, x, y, z, qx, qy, qz, bidx, best, ng);
+            vox_scan<4>(V, a.g.pts, hd, x, y, z, qx, qy, qz, bidx, best, ng);
             a.idx[gq] = bidx;
             if (a.d2) a.d2[gq] = best;
             n_read = hd.y; n_gather = ng; n_done = 1;

@@ -16,8 +16,9 @@ namespace pcreg {
 #ifdef UPD_THREADS_OVERRIDE
 constexpr int UPD_THREADS = UPD_THREADS_OVERRIDE;
 #else
-constexpr int UPD_THREADS = 384;       // 80 registers x 2 blocks per SM for the fused kernel (measured: 44 ms per C3 step; 512 threads at 64
-#endif                                 // registers spill: 48-53 ms; 512 x 1 block at 128 registers: 45 ms; 256 x 3: 51 ms)
+constexpr int UPD_THREADS = 256;       // fused kernel, C3 step, same-session A/B (threads x blocks per SM, registers): 256 x 2 (128) 38.9 ms;
+#endif                                 // 224 x 2: 40.0; 320 x 2 (96): 40.4; 192 x 2 (168): 42.0; 384 x 2 (80, spills): 44.4; 512 x 1 (128): 45.0;
+                                       // 160 x 2: 47.7; 512 x 2 (64): 48-53; 256 x 3 (80): 51.5; 128 x 2 (212, no spills): 53.7
 #ifndef FUSED_MIN_BLOCKS
 #define FUSED_MIN_BLOCKS 2
 #endif

@@ -34,8 +34,11 @@ __device__ __forceinline__ bool vox_lookup(const VoxView& V, double qx, double q
     return hd.y != 0u;
 }
 
-// Exact nearest neighbour of q among the entries of its voxel's list: FP32 scan (four entries in flight), then the entries
+// Exact nearest neighbour of q among the entries of its voxel's list: FP32 scan (BATCH entries in flight), then the entries
 // inside the FP32 error band -- normally one -- decided in FP64 with the oracle's formula on (d2, original index).
+// BATCH = list entries a thread has in flight per trip: 4 in k_nn_vox (more registers cost it occupancy: C5 25.0 vs 25.9 ms),
+// 8 in the fused kernel (128 registers anyway: C3 37.3 vs 36.3 ms; 2: 41.4)
+template <int BATCH>
 __device__ __forceinline__ void vox_scan(const VoxView& V, const GridPoint* __restrict__ pts, uint2 hd, float x, float y, float z,
                                          double qx, double qy, double qz, int32_t& bidx, double& best, unsigned& n_gather) {
     const float4* __restrict__ L = V.ent + hd.x;
@@ -43,20 +46,16 @@ __device__ __forceinline__ void vox_scan(const VoxView& V, const GridPoint* __re
     const float4 far = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
     float m1 = FLT_MAX, m2 = FLT_MAX;
     int r1 = 0;
-    for (uint32_t k = 0; k < n; k += 4) {
-        const float4 e0 = L[k];
-        const float4 e1 = (k + 1 < n) ? L[k + 1] : far;
-        const float4 e2 = (k + 2 < n) ? L[k + 2] : far;
-        const float4 e3 = (k + 3 < n) ? L[k + 3] : far;
-        float dx, dy, dz, d;
-        dx = e0.x - x; dy = e0.y - y; dz = e0.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e0.w); } else m2 = fminf(m2, d);
-        dx = e1.x - x; dy = e1.y - y; dz = e1.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e1.w); } else m2 = fminf(m2, d);
-        dx = e2.x - x; dy = e2.y - y; dz = e2.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e2.w); } else m2 = fminf(m2, d);
-        dx = e3.x - x; dy = e3.y - y; dz = e3.z - z; d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e3.w); } else m2 = fminf(m2, d);
+    for (uint32_t k = 0; k < n; k += BATCH) {
+        float4 e[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) e[u] = (k + u < n) ? L[k + u] : far;      // BATCH loads in flight
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const float dx = e[u].x - x, dy = e[u].y - y, dz = e[u].z - z;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e[u].w); } else m2 = fminf(m2, d);
+        }
     }
     const float thr = fmaf(m1, 3e-6f, m1) + V.band_abs;
     {
