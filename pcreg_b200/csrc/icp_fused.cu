@@ -28,6 +28,11 @@
 
 namespace pcreg {
 
+#ifndef FUSED_INLINE_SUMS
+#define FUSED_INLINE_SUMS 0     // 1: modes without a trim accumulate the 17 sums inside the NN loop (no sums pass, no second gather).
+#endif                          // Measured SLOWER (C4 polish, 16 384 poses: 592 vs 465 ms): the 34 accumulator registers push the NN loop
+                                // into spills.  Kept as a switch.
+
 __device__ __noinline__ void fused_walk(const GridArgs& a, double qx, double qy, double qz, int32_t warm, int32_t& bidx, double& best) {
     Query Q;
     Q.qx = qx; Q.qy = qy; Q.qz = qz;
@@ -47,6 +52,8 @@ __device__ __noinline__ bool fused_pose_update(const double (&s)[KABSCH_NSUMS], 
     return true;
 }
 
+// KNN = the trimmed mode (its selection scratch -- 18 KB of shared memory -- exists only in that instantiation).
+template <bool KNN>
 __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(const __grid_constant__ FusedArgs a) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ double Ts[16];
@@ -64,7 +71,8 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
     const VoxView& V = a.g.vox;
     const GridPoint* __restrict__ pts = a.g.g.pts;
     const bool reject = a.thDist2 > 0.0;
-    const bool knn = a.mode == PCREG_ICP_KNN;
+    constexpr bool knn = KNN;
+    constexpr bool two_pass = KNN || !FUSED_INLINE_SUMS;      // sums in a pass of their own (needed after a trim selection)
     const double px = a.pivot[0], py = a.pivot[1], pz = a.pivot[2];
     unsigned long long c_read = 0, c_gather = 0, c_walk = 0;
     long long t_nn = 0, t_sel = 0, t_sum = 0, t_svd = 0, t_mark = 0;       // phase clocks of thread 0 (profiling only)
@@ -79,6 +87,21 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
         // ---- exact nearest neighbours of the hypothesis' ns queries (two per trip: their header / entry loads overlap) ----
         long long nkept = 0;
         unsigned long long kmin = ~0ull, kmax = 0ull;
+        double s[KABSCH_NSUMS];
+#pragma unroll
+        for (int k = 0; k < KABSCH_NSUMS; ++k) s[k] = 0.0;
+        long long n_used = 0;
+        unsigned long long vK = 0ull;
+        bool all_eq = false;
+        auto weight_of = [&](int i, int32_t j, double d) -> double {
+            const bool keep = j >= 0 && (!reject || d < a.thDist2);
+            double w = 0.0;
+            if (knn) w = (j >= 0 && key_selected(keys_s[i], vK, all_eq)) ? 1.0 : 0.0;
+            else if (a.mode == PCREG_ICP_PLAIN) w = keep ? 1.0 : 0.0;
+            else if (keep) w = fmax(__dsub_rn(a.R_w, __dsqrt_rn(d)), 0.0);
+            if (a.w_src) w = __dmul_rn(w, a.w_src[i]);
+            return w;
+        };
         if (timing) t_mark = clock64();
         for (int i0 = tid; i0 < ns; i0 += 2 * UPD_THREADS) {
             const int i1 = i0 + UPD_THREADS;
@@ -94,14 +117,28 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
             int32_t b0 = -1, b1 = -1;
             double d0 = INFINITY, d1 = INFINITY;
             unsigned ng = 0;
-            if (ok0) { vox_scan<8>(V, pts, hd0, x0, y0, z0, q0x, q0y, q0z, b0, d0, ng); c_read += hd0.y; c_gather += ng; }
+            double w0c[3], w1c[3];                               // the winners' coordinates (modes without a trim: sums right here)
+            if (ok0) { vox_scan<8>(V, pts, hd0, x0, y0, z0, q0x, q0y, q0z, b0, d0, ng, two_pass ? nullptr : w0c); c_read += hd0.y; c_gather += ng; }
             else     { fused_walk(a.g, q0x, q0y, q0z, it > 0 ? idx_s[i0] : -1, b0, d0); ++c_walk; }
             if (has1) {
-                if (ok1) { vox_scan<8>(V, pts, hd1, x1, y1, z1, q1x, q1y, q1z, b1, d1, ng); c_read += hd1.y; c_gather += ng; }
+                if (ok1) { vox_scan<8>(V, pts, hd1, x1, y1, z1, q1x, q1y, q1z, b1, d1, ng, two_pass ? nullptr : w1c); c_read += hd1.y; c_gather += ng; }
                 else     { fused_walk(a.g, q1x, q1y, q1z, it > 0 ? idx_s[i1] : -1, b1, d1); ++c_walk; }
             }
             idx_s[i0] = b0;
             if (has1) idx_s[i1] = b1;
+            if (!two_pass) {
+                ModelPointD m;
+                if (ok0) { m.x = w0c[0]; m.y = w0c[1]; m.z = w0c[2]; m.pad = 0.0; } else m = a.g.md[b0 >= 0 ? b0 : 0];
+                const double w0 = weight_of(i0, b0, d0);
+                if (w0 > 0.0) ++n_used;
+                icp_accumulate(s, w0, d0, q0x, q0y, q0z, m, px, py, pz);
+                if (has1) {
+                    if (ok1) { m.x = w1c[0]; m.y = w1c[1]; m.z = w1c[2]; m.pad = 0.0; } else m = a.g.md[b1 >= 0 ? b1 : 0];
+                    const double w1 = weight_of(i1, b1, d1);
+                    if (w1 > 0.0) ++n_used;
+                    icp_accumulate(s, w1, d1, q1x, q1y, q1z, m, px, py, pz);
+                }
+            }
             if (knn) {
                 const bool keep0 = b0 >= 0 && (!reject || d0 < a.thDist2);
                 const unsigned long long key0 = keep0 ? dbits(__dsqrt_rn(d0)) : KEY_NOSEL;
@@ -118,8 +155,6 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
         __syncthreads();
         if (timing) { const long long t = clock64(); t_nn += t - t_mark; t_mark = t; }
         // ---- trim: the round(k_frac * kept) smallest residuals, stable tie rule (AlignPoints_KNN.m:20-26) ----
-        unsigned long long vK = 0ull;
-        bool all_eq = false;
         if (knn) {
             nkept = block_sum_ll(nkept, redll);
             const int lane = tid & 31, warp = tid >> 5;
@@ -143,28 +178,17 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
         }
         if (timing) { const long long t = clock64(); t_sel += t - t_mark; t_mark = t; }
         // ---- weights + the 17 sums (thread t: correspondences t, t + UPD_THREADS, ... in this order, as k_icp_update) ----
-        double s[KABSCH_NSUMS];
-#pragma unroll
-        for (int k = 0; k < KABSCH_NSUMS; ++k) s[k] = 0.0;
-        long long n_used = 0;
-        auto weight_of = [&](int i, int32_t j, double d) -> double {
-            const bool keep = j >= 0 && (!reject || d < a.thDist2);
-            double w = 0.0;
-            if (a.mode == PCREG_ICP_PLAIN) w = keep ? 1.0 : 0.0;
-            else if (knn) w = (j >= 0 && key_selected(keys_s[i], vK, all_eq)) ? 1.0 : 0.0;
-            else if (keep) w = fmax(__dsub_rn(a.R_w, __dsqrt_rn(d)), 0.0);
-            if (a.w_src) w = __dmul_rn(w, a.w_src[i]);
-            return w;
-        };
-        for (int i = tid; i < ns; i += UPD_THREADS) {
-            const int32_t j = idx_s[i];
-            double qx, qy, qz;
-            quick_tf(Ts, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
-            const ModelPointD m = a.g.md[j >= 0 ? j : 0];
-            const double d = j >= 0 ? dist2_exact(m.x, m.y, m.z, qx, qy, qz) : (double)INFINITY;      // the NN step's d2, bit for bit
-            const double w = weight_of(i, j, d);
-            if (w > 0.0) ++n_used;
-            icp_accumulate(s, w, d, qx, qy, qz, m, px, py, pz);
+        if (two_pass) {
+            for (int i = tid; i < ns; i += UPD_THREADS) {
+                const int32_t j = idx_s[i];
+                double qx, qy, qz;
+                quick_tf(Ts, a.sx[i], a.sy[i], a.sz[i], qx, qy, qz);
+                const ModelPointD m = a.g.md[j >= 0 ? j : 0];
+                const double d = j >= 0 ? dist2_exact(m.x, m.y, m.z, qx, qy, qz) : (double)INFINITY;      // the NN step's d2, bit for bit
+                const double w = weight_of(i, j, d);
+                if (w > 0.0) ++n_used;
+                icp_accumulate(s, w, d, qx, qy, qz, m, px, py, pz);
+            }
         }
         block_sum<KABSCH_NSUMS>(s, red);
         n_used = block_sum_ll(n_used, redll);
@@ -218,14 +242,19 @@ bool icp_fused_eligible(const pcreg_model* m, int64_t ns, int64_t nhyp, const pc
     if (nhyp < ctx().sm_count) return false;
     if (ns >= ((int64_t)1 << 30)) return false;
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, k_icp_fused) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaFuncGetAttributes(&fa, k_icp_fused<true>) != cudaSuccess) { cudaGetLastError(); return false; }
     return icp_fused_smem(ns, o.mode) + fa.sharedSizeBytes + 1024 <= ctx().smem_optin;
 }
 
 void icp_fused_launch(FusedArgs& a, int64_t nhyp, cudaStream_t st) {
     const size_t dyn = icp_fused_smem(a.ns, a.mode);
-    PCREG_CUDA(cudaFuncSetAttribute(k_icp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    k_icp_fused<<<(unsigned)nhyp, UPD_THREADS, dyn, st>>>(a);
+    if (a.mode == PCREG_ICP_KNN) {
+        PCREG_CUDA(cudaFuncSetAttribute(k_icp_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        k_icp_fused<true><<<(unsigned)nhyp, UPD_THREADS, dyn, st>>>(a);
+    } else {
+        PCREG_CUDA(cudaFuncSetAttribute(k_icp_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        k_icp_fused<false><<<(unsigned)nhyp, UPD_THREADS, dyn, st>>>(a);
+    }
     PCREG_LAUNCHED();
 }
 

@@ -40,7 +40,8 @@ __device__ __forceinline__ bool vox_lookup(const VoxView& V, double qx, double q
 // 8 in the fused kernel (128 registers anyway: C3 37.3 vs 36.3 ms; 2: 41.4)
 template <int BATCH>
 __device__ __forceinline__ void vox_scan(const VoxView& V, const GridPoint* __restrict__ pts, uint2 hd, float x, float y, float z,
-                                         double qx, double qy, double qz, int32_t& bidx, double& best, unsigned& n_gather) {
+                                         double qx, double qy, double qz, int32_t& bidx, double& best, unsigned& n_gather,
+                                         double* win = nullptr /* optional: the winner's coordinates [3] */) {
     const float4* __restrict__ L = V.ent + hd.x;
     const uint32_t n = hd.y;
     const float4 far = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
@@ -62,6 +63,7 @@ __device__ __forceinline__ void vox_scan(const VoxView& V, const GridPoint* __re
         const GridPoint gp = pts[r1];
         best = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
         bidx = gp.orig;
+        if (win) { win[0] = gp.x; win[1] = gp.y; win[2] = gp.z; }
     }
     n_gather = 1;
     if (m2 <= thr) {                                     // more than one entry inside the FP32 error band: decide in FP64
@@ -73,7 +75,10 @@ __device__ __forceinline__ void vox_scan(const VoxView& V, const GridPoint* __re
             if (d <= thr && r != r1) {
                 const GridPoint gp = pts[r];
                 const double dd = dist2_exact(gp.x, gp.y, gp.z, qx, qy, qz);
-                if (dd < best || (dd == best && gp.orig < bidx)) { best = dd; bidx = gp.orig; }
+                if (dd < best || (dd == best && gp.orig < bidx)) {
+                    best = dd; bidx = gp.orig;
+                    if (win) { win[0] = gp.x; win[1] = gp.y; win[2] = gp.z; }
+                }
                 ++n_gather;
             }
         }
