@@ -53,7 +53,7 @@ WORKLOADS = {
     "c2g": dict(nm=500_000, ns=10_000, hyp=1, iters=100, mode="weighted", nn="grid", rot=1, trans=(1, 1, 1), max_deg=0.0,
                 sigma=0.3, seed=1002, desc="C2 with the grid NN path (same inputs and results as C2, what a user would run)"),
     # one GPU's share of BASELINE.json configs[4] (16k hypotheses over 8 GPUs): the model (512 MB of points + grid) is NOT
-    # L2-resident and too dense for the voxel-map budget: pyramid walk + row scan + candidate lists (nn_grid.cu)
+    # L2-resident; band-limited voxel map (15.5 GB) + per-pass kernels (65 536 source points do not fit the fused kernel)
     "c5": dict(nm=16_000_000, ns=65536, hyp=2048, iters=20, mode="knn", nn="grid", rot=8, trans=(8, 8, 4), max_deg=10.0,
                sigma=0.3, seed=1005, src_stride=16,
                desc="C5 large upsampled model: 2048 poses/GPU x 65 536 src vs 16M model, KNN-trimmed, 20 it, grid NN"),
