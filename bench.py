@@ -597,6 +597,38 @@ def c4_workload(P, torch, steps=2):
                 total_ms=ransac_ms + r["ms_per_step"], hyp_per_s_end_to_end=c["hyp"] / ((ransac_ms + r["ms_per_step_e2e"]) * 1e-3))
 
 
+def local_points_workload(P, torch, nk=100_000, nm=16_000_000):
+    """Row f2 at the descriptor stage's full size (getSpacialHistogramDescriptors.m:50-60 on the upsampled cloud): 10^5 keypoints
+    against a 16 M-point resident model, R = 3.5, 30..6000 points, through the C ABI with host buffers.  Models with a grid walk
+    the ball's cell rows; the brute-force compaction of grid-less models is timed beside it on 1/50 of the keypoints."""
+    from pcreg_b200 import synth
+    model = np.asarray(synth.make_model(nm, 1005), dtype=np.float64)
+    g = synth.rng(77)
+    kp = model[g.integers(0, nm, nk)] + g.normal(0, 0.3, (nk, 3))
+    out = dict(workload="getLocalPoints: %d keypoints x %d-point model, host-buffer calls (count pass R=3.5/30/6000; count+fill R=1.2)" % (nk, nm))
+    mg = P.Model(model, grid=True, voxel_map=-1)
+    P.getLocalPoints_batch(mg, kp[:64], 3.5, 30, 6000)
+    t0 = time.perf_counter()
+    r = P.getLocalPoints_batch(mg, kp, 3.5, 30, 6000)
+    out["grid_R3.5_ms"] = (time.perf_counter() - t0) * 1e3
+    out["grid_R3.5_accepted"] = int(sum(1 for x in r if x[0] is not None))
+    t0 = time.perf_counter()
+    r = P.getLocalPoints_batch(mg, kp, 1.2, 30, 6000)
+    out["grid_R1.2_ms"] = (time.perf_counter() - t0) * 1e3
+    out["grid_R1.2_accepted"] = int(sum(1 for x in r if x[0] is not None))
+    out["grid_R1.2_points_out"] = int(sum(x[0].shape[0] for x in r if x[0] is not None))
+    sub = kp[:: 50]
+    mb = P.Model(model)
+    P.getLocalPoints_batch(mb, sub[:64], 1.2, 30, 6000)
+    t0 = time.perf_counter()
+    rb = P.getLocalPoints_batch(mb, sub, 1.2, 30, 6000)
+    out["brute_R1.2_ms_for_%d_keypoints" % sub.shape[0]] = (time.perf_counter() - t0) * 1e3
+    out["grid_equals_brute"] = bool(all((a[0] is None and b[0] is None) or (a[0] is not None and b[0] is not None and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]))
+                                        for a, b in zip(r[::50], rb)))
+    mg.destroy(); mb.destroy()
+    return out
+
+
 def side_leg(line, key, fn):
     t0 = time.perf_counter()
     try:
@@ -616,7 +648,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     for name, what in (("c2", "C2 (brute-force) measurement"), ("cpu", "cpu_baseline leg"), ("match", "getMatches (row f4) measurement"),
                        ("c4", "C4 (RANSAC-seeded refinement) leg"), ("c5", "C5 (16M-point model) leg"), ("align", "AlignPoints-batch leg"),
-                       ("strong", "strong-scaling leg at N > 1"), ("e2e-multi", "single-process multi-device e2e leg at N > 1")):
+                       ("local", "getLocalPoints (row f2) leg"), ("strong", "strong-scaling leg at N > 1"), ("e2e-multi", "single-process multi-device e2e leg at N > 1")):
         ap.add_argument("--no-" + name, action="store_true", help="skip the " + what)
     ap.add_argument("--only", action="store_true", help="headline only (all side legs off)")
     args = ap.parse_args()
@@ -709,6 +741,8 @@ def main():
             side_leg(line, "align_batch", lambda: align_batch_workload(P, torch))
         if not off("c4"):
             side_leg(line, "c4", lambda: c4_workload(P, torch))
+        if not off("local"):
+            side_leg(line, "local_points", lambda: local_points_workload(P, torch))
         if not off("c5"):
             def c5_leg():
                 w5 = WORKLOADS["c5"]

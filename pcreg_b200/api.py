@@ -193,7 +193,8 @@ def getSpacialHistogramDescriptors(pts, sample_pts, options, return_status=False
     N x 3 cloud (uploaded for the call, as the reference signature has it) or a resident Model; `options` is the
     reference's struct as a dict: min_pts, max_pts, R, thVar, k ('all' or a fraction), ALIGN_POINTS."""
     own = not isinstance(pts, Model)
-    m = Model(pts) if own else pts
+    # an uploaded cloud gets the uniform grid (no voxel map) when it is large: getLocalPoints then walks the ball's cell rows
+    m = Model(pts, grid=np.shape(pts)[0] >= 200_000, voxel_map=-1) if own else pts
     try:
         kp = np.asfortranarray(np.asarray(sample_pts, dtype=np.float64).reshape(-1, 3))
         nk = kp.shape[0]

@@ -5,10 +5,18 @@
 // c_k, in ORIGINAL model order (:26-28), and "[]" (status 1) when the count is outside [min_points, max_points]
 // (:17-19,31-34; the cube pre-filter of :8-15 contains the sphere, so it never changes the result).
 //
-// Order-preserving brute-force compaction: a warp owns a chunk of 2048 consecutive model points and a tile of 32
-// centres; the hit mask of every (32-point group, centre) is a ballot, running per-centre offsets live one per
-// lane.  Model points are read once per 32 centres.  FP64 throughout (class double out).
+// Two implementations with identical results:
+//  * models WITH a uniform grid (k_local_grid): one block per centre walks the (y,z) cell rows the ball can reach -- the cells
+//    of a row are one contiguous run of the cell-sorted point array, exactly as the row scan of nn_grid.cu uses them --
+//    tests every point of those runs exactly, and (fill pass) sorts the hits by ORIGINAL index in shared memory so that the
+//    neighbourhood comes out in model order like the reference's masked indexing.  Cost ~ points inside the ball's bounding
+//    rows, not N_model: 10^5 keypoints on a 16 M-point model are tens of milliseconds instead of a minute.
+//  * models without a grid (k_local_points): order-preserving brute-force compaction -- a warp owns a chunk of 2048
+//    consecutive model points and a tile of 32 centres; the hit mask of every (32-point group, centre) is a ballot, running
+//    per-centre offsets live one per lane.  Model points are read once per 32 centres.
+// FP64 throughout (class double out); the membership test is the same function in both.
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -95,6 +103,196 @@ __global__ void k_local_scan(const int32_t* __restrict__ cnt, int nchunks, int64
     if (totals) totals[k] = acc;
 }
 
+// ---- grid path ---------------------------------------------------------------------------------------------------------
+constexpr int LPG_THREADS = 256;
+constexpr int LPG_MAX_HITS = 32768;         // hits of one centre the fill pass sorts in shared memory (the reference caps at 6000)
+
+struct LocalGridArgs {
+    GridView g;
+    const ModelPointD* md;
+    const double* cx; const double* cy; const double* cz; int64_t nc;
+    double R;
+    int64_t* totals;                    // count pass: hits per centre
+    const int64_t* offsets;             // fill pass: rows of centre k = offsets[k] .. offsets[k+1]-1
+    const int32_t* status;              // fill pass: centres with status != 0 are skipped (may be null)
+    double* out; int64_t ld_out; double* dists; int32_t* orig;
+    int sort_cap;                       // fill pass: power of two >= the largest accepted count
+};
+
+// distance from v to the slab [lo, lo + w] along one axis (0 inside), minus a rounding allowance: never too large
+__device__ __forceinline__ double slab_dist(double v, double lo, double w) {
+    const double d = fmax(fmax(lo - v, v - (lo + w)), 0.0);
+    return fmax(d - 1e-9 * (fabs(v) + fabs(lo) + w), 0.0);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(LPG_THREADS) k_local_grid(const __grid_constant__ LocalGridArgs a) {
+    extern __shared__ int32_t s_hits[];                      // FILL: original indices of the hits (sorted at the end)
+    __shared__ int32_t s_start[LPG_THREADS];
+    __shared__ int32_t s_incl[LPG_THREADS];
+    __shared__ int32_t s_warp[LPG_THREADS / 32];
+    __shared__ unsigned int s_n;
+    const GridView& G = a.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t k = blockIdx.x;
+    int64_t row0 = 0, nk = 0;
+    if (FILL) {
+        if (a.status && a.status[k] != 0) return;
+        row0 = a.offsets[k];
+        nk = a.offsets[k + 1] - row0;
+        if (nk <= 0) return;
+    }
+    const double cx = a.cx[k], cy = a.cy[k], cz = a.cz[k];
+    const double R = a.R, R2 = R * R, R2lo = R2 * (1.0 - 1e-15), R2hi = R2 * (1.0 + 1e-15);
+    const double cell = G.cell;
+    // cell span of the ball's bounding cube, one cell of slack, clamped to the grid (a point may sit in the cell next to the
+    // one its coordinates suggest: binning rounds)
+    int lo[3], hi[3];
+    const double cc[3] = {cx, cy, cz};
+    bool any = true;
+    for (int ax = 0; ax < 3; ++ax) {
+        const double l = floor((cc[ax] - R - G.origin[ax]) * G.inv_cell) - 1.0, h = floor((cc[ax] + R - G.origin[ax]) * G.inv_cell) + 1.0;
+        lo[ax] = (int)fmax(l, 0.0);
+        hi[ax] = (int)fmin(h, (double)(G.dims[0][ax] - 1));
+        if (!(l <= (double)(G.dims[0][ax] - 1)) || !(h >= 0.0) || lo[ax] > hi[ax]) any = false;
+    }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    long long my_hits = 0;
+    if (any) {
+        const int nyr = hi[1] - lo[1] + 1;
+        const int64_t nrows = (int64_t)nyr * (hi[2] - lo[2] + 1);
+        const int dx0 = G.dims[0][0], dy0 = G.dims[0][1];
+        for (int64_t rb = 0; rb < nrows; rb += LPG_THREADS) {
+            // ---- one (y,z) cell row per thread: the run of points of the cells the ball can reach in x ----
+            const int64_t r = rb + tid;
+            int32_t start = 0, len = 0;
+            if (r < nrows) {
+                const int iz = lo[2] + (int)(r / nyr), iy = lo[1] + (int)(r % nyr);
+                const double dy = slab_dist(cy, G.origin[1] + (double)iy * cell, cell), dz = slab_dist(cz, G.origin[2] + (double)iz * cell, cell);
+                const double rem = R2hi - dy * dy - dz * dz;
+                if (rem >= 0.0) {
+                    const double rx = sqrt(rem) * (1.0 + 1e-9) + 1e-9 * (fabs(cx) + cell);
+                    const int xa = max(lo[0], (int)fmax(floor((cx - rx - G.origin[0]) * G.inv_cell) - 1.0, 0.0));
+                    const int xb = min(hi[0], (int)fmin(floor((cx + rx - G.origin[0]) * G.inv_cell) + 1.0, (double)(dx0 - 1)));
+                    if (xa <= xb) {
+                        const int64_t c0 = ((int64_t)iz * dy0 + iy) * dx0;
+                        start = G.cell_start[c0 + xa];
+                        len = G.cell_start[c0 + xb + 1] - start;
+                    }
+                }
+            }
+            // ---- block-wide inclusive scan of the run lengths ----
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < warp; ++w) woff += s_warp[w];
+            int total = 0;
+            for (int w = 0; w < LPG_THREADS / 32; ++w) total += s_warp[w];
+            s_start[tid] = start;
+            s_incl[tid] = incl + woff;
+            __syncthreads();
+            // ---- the points of those runs, flattened: consecutive threads take consecutive points ----
+            for (int t = tid; t < total; t += LPG_THREADS) {
+                int lo_r = 0, hi_r = LPG_THREADS - 1;                // first run whose inclusive count exceeds t
+                while (lo_r < hi_r) {
+                    const int mid = (lo_r + hi_r) >> 1;
+                    if (s_incl[mid] > t) hi_r = mid; else lo_r = mid + 1;
+                }
+                const int excl = lo_r > 0 ? s_incl[lo_r - 1] : 0;
+                const GridPoint gp = G.pts[s_start[lo_r] + (t - excl)];
+                const double dx = __dsub_rn(gp.x, cx), dy = __dsub_rn(gp.y, cy), dz = __dsub_rn(gp.z, cz);   // pts - c (getLocalPoints.m:23)
+                double dist = 0.0;
+                if (inside(dx, dy, dz, R, R2lo, R2hi, dist)) {
+                    if (FILL) {
+                        const unsigned at = atomicAdd(&s_n, 1u);
+                        if (at < (unsigned)a.sort_cap) s_hits[at] = gp.orig;
+                    } else {
+                        ++my_hits;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (!FILL) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
+        __shared__ long long s_cnt[LPG_THREADS / 32];
+        if (lane == 0) s_cnt[warp] = my_hits;
+        __syncthreads();
+        if (tid == 0) {
+            long long t = 0;
+            for (int w = 0; w < LPG_THREADS / 32; ++w) t += s_cnt[w];
+            a.totals[k] = t;
+        }
+        return;
+    }
+    // ---- fill: sort the hits by original index (bitonic, shared memory), then write them in model order ----
+    const int n = (int)min((unsigned)a.sort_cap, s_n);
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + tid; i < np2; i += LPG_THREADS) s_hits[i] = 0x7fffffff;
+    __syncthreads();
+    for (int kk = 2; kk <= np2; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += LPG_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int32_t x = s_hits[i], y = s_hits[l];
+                    const bool up = (i & kk) == 0;
+                    if ((x > y) == up) { s_hits[i] = y; s_hits[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int j = tid; j < n && j < nk; j += LPG_THREADS) {
+        const int32_t o = s_hits[j];
+        const ModelPointD p = a.md[o];
+        const double dx = __dsub_rn(p.x, cx), dy = __dsub_rn(p.y, cy), dz = __dsub_rn(p.z, cz);
+        double dist = 0.0;
+        inside(dx, dy, dz, R, R2lo, R2hi, dist);
+        const int64_t row = row0 + j;
+        a.out[row] = dx; a.out[a.ld_out + row] = dy; a.out[2 * a.ld_out + row] = dz;
+        if (a.dists) a.dists[row] = dist;
+        if (a.orig) a.orig[row] = o;
+    }
+}
+
+// the grid path pays when the ball's bounding rows are a small part of the grid
+static bool local_grid_worthwhile(const pcreg_model* m, double R) {
+    if (!m->has_grid) return false;
+    if (const char* e = getenv("PCREG_LOCAL_GRID")) { if (e[0] == '0') return false; }
+    const GridView& G = m->grid;
+    const double span = 2.0 * R * G.inv_cell + 3.0;
+    return span * span <= 0.25 * (double)G.dims[0][1] * (double)G.dims[0][2] || m->n > 4000000;
+}
+static void local_grid_count(const pcreg_model* m, const double* d_c, int64_t nc, double R, int64_t* d_totals, cudaStream_t st) {
+    LocalGridArgs a{};
+    a.g = m->grid; a.md = m->md.p; a.cx = d_c; a.cy = d_c + nc; a.cz = d_c + 2 * nc; a.nc = nc; a.R = R; a.totals = d_totals;
+    k_local_grid<false><<<(unsigned)nc, LPG_THREADS, 0, st>>>(a);
+    PCREG_LAUNCHED();
+}
+static void local_grid_fill(const pcreg_model* m, const double* d_c, int64_t nc, double R, const int64_t* d_offsets, const int32_t* d_status,
+                            int64_t max_count, double* d_out, int64_t ld_out, double* d_dists, int32_t* d_orig, cudaStream_t st) {
+    LocalGridArgs a{};
+    a.g = m->grid; a.md = m->md.p; a.cx = d_c; a.cy = d_c + nc; a.cz = d_c + 2 * nc; a.nc = nc; a.R = R;
+    a.offsets = d_offsets; a.status = d_status; a.out = d_out; a.ld_out = ld_out; a.dists = d_dists; a.orig = d_orig;
+    int cap = 32;
+    while (cap < max_count) cap <<= 1;
+    a.sort_cap = cap;
+    const size_t dyn = (size_t)cap * sizeof(int32_t);
+    PCREG_CUDA(cudaFuncSetAttribute(k_local_grid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_local_grid<true><<<(unsigned)nc, LPG_THREADS, dyn, st>>>(a);
+    PCREG_LAUNCHED();
+}
+
 static void local_points_run(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, double R, bool fill,
                              const int64_t* offsets, const int32_t* status_in, int64_t* counts_out, double* pts_rel, int64_t ld_out,
                              double* dists, int32_t* orig) {
@@ -105,8 +303,35 @@ static void local_points_run(const pcreg_model* m, const double* centres, int64_
     PCREG_REQUIRE(ntiles <= 65535, "local_points: at most 2,097,120 centres per call");
     DevBuf<double> dc((size_t)nc * 3);
     for (int a = 0; a < 3; ++a) PCREG_CUDA(cudaMemcpyAsync(dc.p + a * nc, centres + a * ld, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
-    DevBuf<int32_t> cnt((size_t)ntiles * LP_TILE * nchunks);
     DevBuf<int64_t> totals((size_t)nc);
+    // ---- models with a grid: walk the ball's cell rows instead of the whole model ----
+    int64_t max_count = 0;
+    if (fill) for (int64_t k = 0; k < nc; ++k) if (!status_in || status_in[k] == 0) max_count = std::max(max_count, offsets[k + 1] - offsets[k]);
+    if (local_grid_worthwhile(m, R) && (!fill || max_count <= LPG_MAX_HITS)) {
+        if (!fill) {
+            local_grid_count(m, dc.p, nc, R, totals.p, st);
+            PCREG_CUDA(cudaMemcpyAsync(counts_out, totals.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+            PCREG_CUDA(cudaStreamSynchronize(st));
+            return;
+        }
+        const int64_t ntotal = offsets[nc];
+        PCREG_REQUIRE(ntotal >= 0 && ld_out >= ntotal, "local_points_fill: bad offsets / ld_out");
+        const size_t nel = (size_t)std::max<int64_t>(ntotal, 1);
+        DevBuf<int64_t> d_off((size_t)nc + 1);
+        DevBuf<int32_t> d_st(status_in ? (size_t)nc : 0), d_orig(orig ? nel : 0);
+        DevBuf<double> d_out(nel * 3), d_dist(dists ? nel : 0);
+        PCREG_CUDA(cudaMemcpyAsync(d_off.p, offsets, ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (status_in) PCREG_CUDA(cudaMemcpyAsync(d_st.p, status_in, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+        local_grid_fill(m, dc.p, nc, R, d_off.p, status_in ? d_st.p : nullptr, max_count, d_out.p, (int64_t)nel, dists ? d_dist.p : nullptr,
+                        orig ? d_orig.p : nullptr, st);
+        for (int k = 0; k < 3; ++k)
+            PCREG_CUDA(cudaMemcpyAsync(pts_rel + (size_t)k * ld_out, d_out.p + k * nel, (size_t)ntotal * 8, cudaMemcpyDeviceToHost, st));
+        if (dists) PCREG_CUDA(cudaMemcpyAsync(dists, d_dist.p, (size_t)ntotal * 8, cudaMemcpyDeviceToHost, st));
+        if (orig) PCREG_CUDA(cudaMemcpyAsync(orig, d_orig.p, (size_t)ntotal * 4, cudaMemcpyDeviceToHost, st));
+        PCREG_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    DevBuf<int32_t> cnt((size_t)ntiles * LP_TILE * nchunks);
     LocalArgs a{};
     a.md = m->md.p; a.n = m->n; a.cx = dc.p; a.cy = dc.p + nc; a.cz = dc.p + 2 * nc; a.nc = nc; a.R = R;
     a.chunk_cnt = cnt.p; a.nchunks = nchunks;
@@ -150,16 +375,21 @@ void local_points_device(const pcreg_model* m, const double* centres, int64_t nc
     PCREG_REQUIRE(ntiles <= 65535, "local_points: at most 2,097,120 centres per call");
     DevBuf<double> dc((size_t)nc * 3);
     for (int a = 0; a < 3; ++a) PCREG_CUDA(cudaMemcpyAsync(dc.p + a * nc, centres + a * ld, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
-    DevBuf<int32_t> cnt((size_t)ntiles * LP_TILE * nchunks);
     DevBuf<int64_t> totals((size_t)nc);
+    const bool use_grid = local_grid_worthwhile(m, R);
+    DevBuf<int32_t> cnt(use_grid ? 0 : (size_t)ntiles * LP_TILE * nchunks);
     LocalArgs a{};
     a.md = m->md.p; a.n = m->n; a.cx = dc.p; a.cy = dc.p + nc; a.cz = dc.p + 2 * nc; a.nc = nc; a.R = R;
     a.chunk_cnt = cnt.p; a.nchunks = nchunks;
     dim3 grid((unsigned)nchunks, (unsigned)ntiles);
-    k_local_points<false><<<grid, 32, 0, st>>>(a);
-    PCREG_LAUNCHED();
-    k_local_scan<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(cnt.p, nchunks, nc, nullptr, nullptr, nullptr, totals.p);
-    PCREG_LAUNCHED();
+    if (use_grid) {
+        local_grid_count(m, dc.p, nc, R, totals.p, st);
+    } else {
+        k_local_points<false><<<grid, 32, 0, st>>>(a);
+        PCREG_LAUNCHED();
+        k_local_scan<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(cnt.p, nchunks, nc, nullptr, nullptr, nullptr, totals.p);
+        PCREG_LAUNCHED();
+    }
     out.counts.assign((size_t)nc, 0);
     PCREG_CUDA(cudaMemcpyAsync(out.counts.data(), totals.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
     PCREG_CUDA(cudaStreamSynchronize(st));
@@ -174,10 +404,23 @@ void local_points_device(const pcreg_model* m, const double* centres, int64_t nc
     out.nel = std::max<int64_t>(out.ntotal, 1);
     out.pts.alloc((size_t)out.nel * 3);
     out.d_offsets.alloc((size_t)nc + 1);
-    DevBuf<int64_t> base((size_t)nc * nchunks);
     DevBuf<int32_t> d_st((size_t)nc);
     PCREG_CUDA(cudaMemcpyAsync(out.d_offsets.p, out.offsets.data(), ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
     PCREG_CUDA(cudaMemcpyAsync(d_st.p, out.status.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    int64_t max_count = 0;
+    for (int64_t k = 0; k < nc; ++k) if (!out.status[k]) max_count = std::max(max_count, out.counts[k]);
+    if (use_grid && max_count <= LPG_MAX_HITS) {
+        local_grid_fill(m, dc.p, nc, R, out.d_offsets.p, d_st.p, max_count, out.pts.p, out.nel, nullptr, nullptr, st);
+        PCREG_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    if (use_grid) {                                         // counts came from the grid pass: the brute fill needs its own chunk counts
+        cnt.alloc((size_t)ntiles * LP_TILE * nchunks);
+        a.chunk_cnt = cnt.p;
+        k_local_points<false><<<grid, 32, 0, st>>>(a);
+        PCREG_LAUNCHED();
+    }
+    DevBuf<int64_t> base((size_t)nc * nchunks);
     k_local_scan<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(cnt.p, nchunks, nc, out.d_offsets.p, d_st.p, base.p, nullptr);
     PCREG_LAUNCHED();
     a.chunk_base = base.p; a.out = out.pts.p; a.ld_out = out.nel; a.dists = nullptr; a.orig = nullptr;
