@@ -599,34 +599,59 @@ def c4_workload(P, torch, steps=2):
 
 def local_points_workload(P, torch, nk=100_000, nm=16_000_000):
     """Row f2 at the descriptor stage's full size (getSpacialHistogramDescriptors.m:50-60 on the upsampled cloud): 10^5 keypoints
-    against a 16 M-point resident model, R = 3.5, 30..6000 points, through the C ABI with host buffers.  Models with a grid walk
-    the ball's cell rows; the brute-force compaction of grid-less models is timed beside it on 1/50 of the keypoints."""
-    from pcreg_b200 import synth
+    against a 16 M-point resident model through the C ABI with host buffers.  Models with a grid walk the ball's cell rows;
+    the brute-force compaction of grid-less models is timed beside it on 1/50 of the keypoints."""
+    from pcreg_b200 import synth, _lib as L
     model = np.asarray(synth.make_model(nm, 1005), dtype=np.float64)
     g = synth.rng(77)
     kp = model[g.integers(0, nm, nk)] + g.normal(0, 0.3, (nk, 3))
-    out = dict(workload="getLocalPoints: %d keypoints x %d-point model, host-buffer calls (count pass R=3.5/30/6000; count+fill R=1.2)" % (nk, nm))
+    lib = L.lib()
+
+    def count(m, c, R, mn, mx):
+        cf = np.asfortranarray(c)
+        counts = np.empty(c.shape[0], dtype=np.int64); status = np.empty(c.shape[0], dtype=np.int32)
+        a = (m.handle, cf.ctypes.data_as(L.c_f64p), c.shape[0], c.shape[0], R, mn, mx, counts.ctypes.data_as(L.c_i64p), status.ctypes.data_as(L.c_i32p))
+        L.check(lib.pcreg_local_points_count(*a), "count")
+        t0 = time.perf_counter()
+        L.check(lib.pcreg_local_points_count(*a), "count")
+        return (time.perf_counter() - t0) * 1e3, counts, status
+
+    def fill(m, c, R, counts, status):
+        cf = np.asfortranarray(c)
+        off = np.zeros(c.shape[0] + 1, dtype=np.int64)
+        np.cumsum(np.where(status == 0, counts, 0), out=off[1:])
+        nt = max(int(off[-1]), 1)
+        out = np.zeros((nt, 3), dtype=np.float64, order="F"); d = np.zeros(nt); idx = np.zeros(nt, dtype=np.int32)
+        a = (m.handle, cf.ctypes.data_as(L.c_f64p), c.shape[0], c.shape[0], R, off.ctypes.data_as(L.c_i64p), status.ctypes.data_as(L.c_i32p),
+             out.ctypes.data_as(L.c_f64p), nt, d.ctypes.data_as(L.c_f64p), idx.ctypes.data_as(L.c_i32p))
+        L.check(lib.pcreg_local_points_fill(*a), "fill")
+        t0 = time.perf_counter()
+        L.check(lib.pcreg_local_points_fill(*a), "fill")
+        return (time.perf_counter() - t0) * 1e3, out, d, idx, nt
+
+    res = dict(workload="getLocalPoints: %d keypoints x %d-point model, C-ABI calls with host buffers" % (nk, nm))
     mg = P.Model(model, grid=True, voxel_map=-1)
-    P.getLocalPoints_batch(mg, kp[:64], 3.5, 30, 6000)
-    t0 = time.perf_counter()
-    r = P.getLocalPoints_batch(mg, kp, 3.5, 30, 6000)
-    out["grid_R3.5_ms"] = (time.perf_counter() - t0) * 1e3
-    out["grid_R3.5_accepted"] = int(sum(1 for x in r if x[0] is not None))
-    t0 = time.perf_counter()
-    r = P.getLocalPoints_batch(mg, kp, 1.2, 30, 6000)
-    out["grid_R1.2_ms"] = (time.perf_counter() - t0) * 1e3
-    out["grid_R1.2_accepted"] = int(sum(1 for x in r if x[0] is not None))
-    out["grid_R1.2_points_out"] = int(sum(x[0].shape[0] for x in r if x[0] is not None))
-    sub = kp[:: 50]
+    ms, cnt, st = count(mg, kp, 3.5, 30, 6000)
+    res["count_R3.5"] = dict(ms=ms, keypoints=nk, mean_points_in_ball=float(cnt.mean()), accepted=int((st == 0).sum()),
+                             note="getSpacialHistogramDescriptors.m's options on this density: every ball exceeds max_pts = 6000")
+    ms, cnt, st = count(mg, kp, 1.2, 30, 6000)
+    res["count_R1.2"] = dict(ms=ms, keypoints=nk, mean_points_in_ball=float(cnt.mean()), accepted=int((st == 0).sum()))
+    sub = kp[::10]
+    cs, ss = cnt[::10].copy(), st[::10].copy()
+    ms, o1, d1, i1, nt = fill(mg, sub, 1.2, cs, ss)
+    res["fill_R1.2"] = dict(ms=ms, keypoints=int(sub.shape[0]), points_out=nt, d2h_bytes=nt * 36,
+                            note="the call is its device-to-host copy: 36 B per neighbourhood point into pageable host arrays")
     mb = P.Model(model)
-    P.getLocalPoints_batch(mb, sub[:64], 1.2, 30, 6000)
-    t0 = time.perf_counter()
-    rb = P.getLocalPoints_batch(mb, sub, 1.2, 30, 6000)
-    out["brute_R1.2_ms_for_%d_keypoints" % sub.shape[0]] = (time.perf_counter() - t0) * 1e3
-    out["grid_equals_brute"] = bool(all((a[0] is None and b[0] is None) or (a[0] is not None and b[0] is not None and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]))
-                                        for a, b in zip(r[::50], rb)))
+    few = kp[::50]
+    msb, cb, sb = count(mb, few, 1.2, 30, 6000)
+    res["brute_count_R1.2"] = dict(ms=msb, keypoints=int(few.shape[0]), note="grid-less model: order-preserving brute-force compaction")
+    ms2, o2, d2, i2, nt2 = fill(mb, sub[::5], 1.2, cb, sb)
+    sel = np.concatenate([[0], np.cumsum(np.where(ss == 0, cs, 0))])
+    rows = np.concatenate([np.arange(sel[k], sel[k + 1]) for k in range(0, sub.shape[0], 5)]) if nt2 > 1 else np.arange(0)
+    res["grid_equals_brute"] = bool(np.array_equal(cb, cnt[::50]) and np.array_equal(o1[rows], o2[:rows.size]) and np.array_equal(d1[rows], d2[:rows.size])
+                                    and np.array_equal(i1[rows], i2[:rows.size]))
     mg.destroy(); mb.destroy()
-    return out
+    return res
 
 
 def side_leg(line, key, fn):
