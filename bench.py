@@ -533,12 +533,13 @@ def match_workload(P, torch, n1=3000, n2=20000, dim=980, reps=3):
                               note="2 FP64 instructions per (pair, dimension) term (t = a - b; acc += |t|); peak = measured DFMA issue rate"))
 
 
-def align_batch_workload(P, torch, nb=1500, reps=3):
+def align_batch_workload(P, torch, nb=10_000, reps=2):
     """Rows a1-a5 at the workload of visualizeGTMatches.m:94-141: thousands of neighbourhoods of 500-6000 points through the
     AlignPoints family, one batched call per variant (host buffers).  The kernel streams every neighbourhood: SURVEY.md
     section 8d byte model = 2 passes over the input + 1 output = 3 x 24 B per point (class double)."""
     from pcreg_b200 import synth
-    nbs = synth.make_neighbourhoods(nb, 77)
+    base = synth.make_neighbourhoods((nb + 3) // 4, 77)                         # 4 shifted copies of each: generation is host time
+    nbs = [a + np.array([17.0 * k, -9.0 * k, 4.0 * k]) for k in range(4) for a in base][:nb]
     npts = int(sum(a.shape[0] for a in nbs))
     peak, how = hbm_peak()
     out = {}

@@ -118,10 +118,10 @@ __global__ void __launch_bounds__(UPD_THREADS, FUSED_MIN_BLOCKS) k_icp_fused(con
             double d0 = INFINITY, d1 = INFINITY;
             unsigned ng = 0;
             double w0c[3], w1c[3];                               // the winners' coordinates (modes without a trim: sums right here)
-            if (ok0) { vox_scan<8>(V, pts, hd0, x0, y0, z0, q0x, q0y, q0z, b0, d0, ng, two_pass ? nullptr : w0c); c_read += hd0.y; c_gather += ng; }
+            if (ok0) { vox_scan<8, true>(V, pts, hd0, x0, y0, z0, q0x, q0y, q0z, b0, d0, ng, two_pass ? nullptr : w0c); c_read += hd0.y; c_gather += ng; }
             else     { fused_walk(a.g, q0x, q0y, q0z, it > 0 ? idx_s[i0] : -1, b0, d0); ++c_walk; }
             if (has1) {
-                if (ok1) { vox_scan<8>(V, pts, hd1, x1, y1, z1, q1x, q1y, q1z, b1, d1, ng, two_pass ? nullptr : w1c); c_read += hd1.y; c_gather += ng; }
+                if (ok1) { vox_scan<8, true>(V, pts, hd1, x1, y1, z1, q1x, q1y, q1z, b1, d1, ng, two_pass ? nullptr : w1c); c_read += hd1.y; c_gather += ng; }
                 else     { fused_walk(a.g, q1x, q1y, q1z, it > 0 ? idx_s[i1] : -1, b1, d1); ++c_walk; }
             }
             idx_s[i0] = b0;

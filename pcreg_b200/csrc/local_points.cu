@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(LPG_THREADS) k_local_grid(const __grid_constan
 // the grid path pays when the ball's bounding rows are a small part of the grid
 static bool local_grid_worthwhile(const pcreg_model* m, double R) {
     if (!m->has_grid) return false;
-    if (const char* e = getenv("PCREG_LOCAL_GRID")) { if (e[0] == '0') return false; }
+    static const bool off = [] { const char* e = getenv("PCREG_LOCAL_GRID"); return e && e[0] == '0'; }();   // tuning switch, read once
+    if (off) return false;
     const GridView& G = m->grid;
     const double span = 2.0 * R * G.inv_cell + 3.0;
     return span * span <= 0.25 * (double)G.dims[0][1] * (double)G.dims[0][2] || m->n > 4000000;

@@ -306,8 +306,11 @@ __global__ void __launch_bounds__(256) k_vox_refine(const __grid_constant__ VoxL
                     ++st_long;
                     continue;
                 }
-                if (w_off + cnt > w_end) {                               // reserve more pool space (one atomic per VOX_CHUNK entries)
-                    const unsigned long long need = cnt > (uint32_t)VOX_CHUNK ? (unsigned long long)cnt : (unsigned long long)VOX_CHUNK;
+                // finest level: lists start on even entries and are padded to an even length with a far sentinel, so that the
+                // scan reads PAIRS of entries with one 256-bit load (pcreg_vox.cuh)
+                const uint32_t cnt_al = FINAL ? ((cnt + 1u) & ~1u) : cnt;
+                if (w_off + cnt_al > w_end) {                            // reserve more pool space (one atomic per VOX_CHUNK entries)
+                    const unsigned long long need = cnt_al > (uint32_t)VOX_CHUNK ? (unsigned long long)cnt_al : (unsigned long long)VOX_CHUNK;
                     unsigned long long o = 0;
                     if (lane == 0) o = atomicAdd(a.pool_cursor, need);
                     w_off = __shfl_sync(FULL, o, 0);
@@ -319,7 +322,8 @@ __global__ void __launch_bounds__(256) k_vox_refine(const __grid_constant__ VoxL
                     continue;
                 }
                 const unsigned long long off = w_off;
-                w_off += cnt;
+                w_off += cnt_al;
+                if (FINAL && (cnt & 1u) && lane == 0) a.c_ent[off + cnt] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, __int_as_float(0));
                 // sweep 3: write
                 uint32_t pos = 0;
                 for (uint32_t it = 0; it < nit; ++it) {
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(256) k_nn_vox(const __grid_constant__ GridArgs
         float x, y, z;
         if (vox_lookup(V, qx, qy, qz, hd, x, y, z)) {
             int32_t bidx; double best; unsigned ng;
-            vox_scan<4>(V, a.g.pts, hd, x, y, z, qx, qy, qz, bidx, best, ng);
+            vox_scan<4, false>(V, a.g.pts, hd, x, y, z, qx, qy, qz, bidx, best, ng);
             a.idx[gq] = bidx;
             if (a.d2) a.d2[gq] = best;
             n_read = hd.y; n_gather = ng; n_done = 1;
@@ -489,6 +493,7 @@ void vox_build(pcreg_model* m, const pcreg_model_opts& o, cudaStream_t st) {
         if (is_top) cap = std::min<unsigned long long>(nvox_l * std::min<unsigned long long>((unsigned long long)n, maxlen_of(l)),
                                                        std::max<unsigned long long>(64ull * (unsigned long long)n, 1ull << 26));
         else        cap = 8ull * used + 65536ull * (unsigned long long)VOX_CHUNK;     // a child's list is a subset of its parent's: 8 x is the worst case (+ chunk tails)
+        if (fin && !is_top) cap += 8ull * listed_parent;                                  // + the pad entry of odd lists
         if (fin) cap = std::min<unsigned long long>(cap, (unsigned long long)(budget_bytes / sizeof(float4)));
         cap = std::min<unsigned long long>(std::max<unsigned long long>(cap, 1024ull), 0xfffffff0ull);
         if (fin) ent.alloc((size_t)cap); else c_ids.alloc((size_t)cap);

@@ -34,28 +34,53 @@ __device__ __forceinline__ bool vox_lookup(const VoxView& V, double qx, double q
     return hd.y != 0u;
 }
 
+struct __align__(32) EntPair { float4 a, b; };
+
 // Exact nearest neighbour of q among the entries of its voxel's list: FP32 scan (BATCH entries in flight), then the entries
 // inside the FP32 error band -- normally one -- decided in FP64 with the oracle's formula on (d2, original index).
 // BATCH = list entries a thread has in flight per trip: 4 in k_nn_vox (more registers cost it occupancy: C5 25.0 vs 25.9 ms),
-// 8 in the fused kernel (128 registers anyway: C3 37.3 vs 36.3 ms; 2: 41.4)
-template <int BATCH>
+// 8 in the fused kernel (128 registers anyway: C3 37.3 vs 36.3 ms; 2: 41.4).
+// PAIRED: lists start on even entries and odd ones end with a far sentinel (nn_vox.cu), so two entries can be read with one
+// 256-bit load (LDG.E.256 on sm_100a): half the load instructions -- and L1 wavefronts -- of the scan.  The fused kernel uses
+// it (C3 37.3 -> 35.8 ms per step, C4 481 -> 381 ms per 16 384 poses); k_nn_vox does not: six more registers cost it a block
+// per SM (C5 322 -> 340 ms per step; at the same occupancy with spills 354; C3 per-pass path 18.8 -> 18.0 ms, not worth it).
+// Measured and dropped: reading the last pair again past the end of a list and selecting a far distance instead of the
+// predicated load -- fewer instructions but more loads: C3 35.8 -> 36.6 ms, C4 381 -> 399 ms.  The scan is bound by load
+// wavefronts, not by issue slots.
+template <int BATCH, bool PAIRED>
 __device__ __forceinline__ void vox_scan(const VoxView& V, const GridPoint* __restrict__ pts, uint2 hd, float x, float y, float z,
                                          double qx, double qy, double qz, int32_t& bidx, double& best, unsigned& n_gather,
                                          double* win = nullptr /* optional: the winner's coordinates [3] */) {
     const float4* __restrict__ L = V.ent + hd.x;
     const uint32_t n = hd.y;
-    const float4 far = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
     float m1 = FLT_MAX, m2 = FLT_MAX;
     int r1 = 0;
-    for (uint32_t k = 0; k < n; k += BATCH) {
-        float4 e[BATCH];
+    auto take = [&](const float4 en) {
+        const float dx = en.x - x, dy = en.y - y, dz = en.z - z;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(en.w); } else m2 = fminf(m2, d);
+    };
+    if (PAIRED) {
+        static_assert(BATCH % 2 == 0, "vox_scan: BATCH counts entries, loaded in pairs");
+        const EntPair* __restrict__ L2 = reinterpret_cast<const EntPair*>(L);
+        const uint32_t np = (n + 1u) >> 1;
+        EntPair far;
+        far.a = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f); far.b = far.a;
+        for (uint32_t k = 0; k < np; k += BATCH / 2) {
+            EntPair e[BATCH / 2];
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) e[u] = (k + u < n) ? L[k + u] : far;      // BATCH loads in flight
+            for (int u = 0; u < BATCH / 2; ++u) e[u] = (k + u < np) ? L2[k + u] : far;      // BATCH / 2 loads in flight
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const float dx = e[u].x - x, dy = e[u].y - y, dz = e[u].z - z;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (d < m1) { m2 = m1; m1 = d; r1 = __float_as_int(e[u].w); } else m2 = fminf(m2, d);
+            for (int u = 0; u < BATCH / 2; ++u) { take(e[u].a); take(e[u].b); }
+        }
+    } else {
+        const float4 far = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
+        for (uint32_t k = 0; k < n; k += BATCH) {
+            float4 e[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) e[u] = (k + u < n) ? L[k + u] : far;      // BATCH loads in flight
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) take(e[u]);
         }
     }
     const float thr = fmaf(m1, 3e-6f, m1) + V.band_abs;
