@@ -68,7 +68,7 @@ typedef struct {
     double  voxel_scale;       /* voxel edge in units of the estimated point spacing, <= 0 -> 1.25                   */
     double  voxel_margin;      /* padding around the bounding box (model units); 0 -> 4 % of the largest extent, < 0 -> none.
                                   Queries outside the padded box are answered by the pyramid walk.                    */
-    int64_t max_voxels;        /* cap on the number of voxels, <= 0 -> min(2^27, device memory / 1024 B)             */
+    int64_t max_voxels;        /* cap on the number of voxels, <= 0 -> min(2^28, device memory / 512 B); denser models get a band-limited map */
 } pcreg_model_opts;
 
 /* Upload a model cloud (the dense CT/MRI cloud every driver loads once: completeExperiment.m:15,
