@@ -57,12 +57,21 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 3 : 1) k_icp_update(const __gr
         unsigned long long* __restrict__ keys = a.keys + h * ns;
         long long nkept = 0;
         unsigned long long kmin = ~0ull, kmax = 0ull;
-        for (int64_t i = tid; i < ns; i += NT) {
-            const double d = d2[i];
-            const bool keep = idx[i] >= 0 && (!reject || d < a.thDist2);
-            const unsigned long long key = keep ? dbits(__dsqrt_rn(d)) : KEY_NOSEL;
-            keys[i] = key;
-            if (keep) { ++nkept; kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
+        constexpr int KU = 4;                                  // residuals / indices of a trip are loaded before any is used
+        for (int64_t i0 = tid; i0 < ns; i0 += (int64_t)KU * NT) {
+            double dv[KU]; int32_t jv[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) { const int64_t i = i0 + (int64_t)u * NT; const bool ok = i < ns; dv[u] = ok ? d2[i] : 0.0; jv[u] = ok ? idx[i] : -1; }
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int64_t i = i0 + (int64_t)u * NT;
+                if (i >= ns) break;
+                const double d = dv[u];
+                const bool keep = jv[u] >= 0 && (!reject || d < a.thDist2);
+                const unsigned long long key = keep ? dbits(__dsqrt_rn(d)) : KEY_NOSEL;
+                keys[i] = key;
+                if (keep) { ++nkept; kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
+            }
         }
         nkept = block_sum_ll(nkept, redll);
         {   // block min / max of the kept keys
@@ -111,21 +120,27 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 3 : 1) k_icp_update(const __gr
         if (a.w_src) w = __dmul_rn(w, a.w_src[i]);
         return w;
     };
+    // The correspondence indices of a trip are loaded one trip AHEAD: the model gathers -- the only loads that depend on
+    // another load -- then go out at the top of the trip together with everything else (one memory latency per trip, not two).
     constexpr int UB = 4;
+    int32_t jn[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) { const int64_t i = (int64_t)tid + (int64_t)u * NT; jn[u] = i < ns ? idx[i] : -1; }
     for (int64_t i0 = tid; i0 < ns; i0 += (int64_t)UB * NT) {
         int32_t jj[UB]; double dd[UB], xs[UB], ys[UB], zs[UB], ww[UB];
         ModelPointD mm[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) { jj[u] = jn[u]; mm[u] = a.md[jj[u] >= 0 ? jj[u] : 0]; }
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const int64_t i = i0 + (int64_t)u * NT;
             const bool ok = i < ns;
             const int64_t ic = ok ? i : tid;                 // tid < ns is guaranteed inside the loop
-            jj[u] = ok ? idx[ic] : -1;
             dd[u] = d2[ic];
             xs[u] = a.sx[ic]; ys[u] = a.sy[ic]; zs[u] = a.sz[ic];
+            const int64_t in = i + (int64_t)UB * NT;
+            jn[u] = in < ns ? idx[in] : -1;
         }
-#pragma unroll
-        for (int u = 0; u < UB; ++u) mm[u] = a.md[jj[u] >= 0 ? jj[u] : 0];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const int64_t i = i0 + (int64_t)u * NT;

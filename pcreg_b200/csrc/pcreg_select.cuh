@@ -14,6 +14,9 @@ namespace pcreg {
 
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_CAP = 1024;
+#ifndef SEL_UNROLL
+#define SEL_UNROLL 4
+#endif
 
 struct HistSelShared {
     int hist[SEL_BINS];
@@ -44,12 +47,20 @@ __device__ __forceinline__ void block_hist_select(unsigned long long* __restrict
         for (int b = tid; b < SEL_BINS; b += nthr) sh.hist[b] = 0;
         if (tid == 0) sh.ncand = 0;
         __syncthreads();
-        for (long long i = tid; i < n; i += nthr) {
-            const unsigned long long key = keys[i];
-            if (key == KEY_NOSEL) continue;
-            int b = (int)((__longlong_as_double((long long)key) - rmin) * scale);
-            b = b < 0 ? 0 : (b >= SEL_BINS ? SEL_BINS - 1 : b);
-            atomicAdd(&sh.hist[b], 1);
+        // SEL_UNROLL keys per trip, loaded before any is used: with keys in global memory (k_icp_update) a pass over them is
+        // bound by the load latency of one key per thread otherwise
+        for (long long i0 = tid; i0 < n; i0 += (long long)SEL_UNROLL * nthr) {
+            unsigned long long kk[SEL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SEL_UNROLL; ++u) { const long long i = i0 + (long long)u * nthr; kk[u] = i < n ? keys[i] : KEY_NOSEL; }
+#pragma unroll
+            for (int u = 0; u < SEL_UNROLL; ++u) {
+                const unsigned long long key = kk[u];
+                if (key == KEY_NOSEL) continue;
+                int b = (int)((__longlong_as_double((long long)key) - rmin) * scale);
+                b = b < 0 ? 0 : (b >= SEL_BINS ? SEL_BINS - 1 : b);
+                atomicAdd(&sh.hist[b], 1);
+            }
         }
         __syncthreads();
         if (tid < 32) {                                   // warp 0: find the bin where the cumulative count reaches K
@@ -76,14 +87,20 @@ __device__ __forceinline__ void block_hist_select(unsigned long long* __restrict
         }
         __syncthreads();
         const int bstar = sh.bin;
-        for (long long i = tid; i < n; i += nthr) {
-            const unsigned long long key = keys[i];
-            if (key == KEY_NOSEL) continue;
-            int b = (int)((__longlong_as_double((long long)key) - rmin) * scale);
-            b = b < 0 ? 0 : (b >= SEL_BINS ? SEL_BINS - 1 : b);
-            if (b == bstar) {
-                const int pos = atomicAdd(&sh.ncand, 1);
-                if (pos < SEL_CAP) sh.cand[pos] = key;
+        for (long long i0 = tid; i0 < n; i0 += (long long)SEL_UNROLL * nthr) {
+            unsigned long long kk[SEL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SEL_UNROLL; ++u) { const long long i = i0 + (long long)u * nthr; kk[u] = i < n ? keys[i] : KEY_NOSEL; }
+#pragma unroll
+            for (int u = 0; u < SEL_UNROLL; ++u) {
+                const unsigned long long key = kk[u];
+                if (key == KEY_NOSEL) continue;
+                int b = (int)((__longlong_as_double((long long)key) - rmin) * scale);
+                b = b < 0 ? 0 : (b >= SEL_BINS ? SEL_BINS - 1 : b);
+                if (b == bstar) {
+                    const int pos = atomicAdd(&sh.ncand, 1);
+                    if (pos < SEL_CAP) sh.cand[pos] = key;
+                }
             }
         }
         __syncthreads();

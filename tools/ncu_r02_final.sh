@@ -11,4 +11,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_nn_vox -s 30 -
 ncu --set full --clock-control none --import-source on -k regex:k_icp_update -s 30 -c 1 -o gpurun_out/r02_full_c5_update -f $B > gpurun_out/ncuB2.log 2>&1
 $C > gpurun_out/plainC.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_nn_brute -s 40 -c 1 -o gpurun_out/r02_full_c2_brute -f $C > gpurun_out/ncuC1.log 2>&1
+D="python tools/local_points_run.py"
+$D > gpurun_out/plainD.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_local_grid -s 1 -c 1 -o gpurun_out/r02_full_local_grid -f $D > gpurun_out/ncuD1.log 2>&1
 ls -la gpurun_out | tail -20
