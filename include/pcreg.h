@@ -271,8 +271,10 @@ int  pcreg_icp_batch(const pcreg_model* m, const void* src, int is_double, int64
 
 /* Same, with every array already resident on the device the library was initialised on
  * (src as float64 column-major, ld = ns) and launched on `stream` (a cudaStream_t passed as
- * void*; NULL = default stream).  Asynchronous: the caller synchronises the stream.  `best` is
- * a device int64.  This is the entry bench.py's device-resident `value` is timed through. */
+ * void*; NULL = default stream).  Nothing crosses PCIe, but the call is SYNCHRONOUS with respect to
+ * `stream`: it returns after its last kernel has finished (its scratch buffers go back to the pool on
+ * return).  `best` is a device int64.  This is the entry bench.py's device-resident `value` is timed
+ * through. */
 int  pcreg_icp_batch_dev(const pcreg_model* m, const double* d_src, int64_t ns,
                          const double* d_w_src, const double* d_T0_16, int64_t nhyp,
                          const pcreg_icp_opts* opts,
