@@ -110,7 +110,7 @@ int  pcreg_quick_tf(const void* pts, int is_double, int64_t n, int64_t ld, const
  *          prefix sum of the counts of the centres with status 0, zero-length for the others) and gets
  *          pts_rel (ntotal x 3 column-major, ld_out), optional dists (vecnorm) and optional original indices.
  * Models created with build_grid = 1 answer from the grid (cost ~ the points near the ball; 10^5 centres on a 16 M-point
- * model: ~20 ms); models without a grid scan the whole cloud per 32 centres.  Same results, bit for bit. */
+ * model: ~14 ms); models without a grid scan the whole cloud per 32 centres.  Same results, bit for bit. */
 int  pcreg_local_points_count(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, double R,
                               int64_t min_points, int64_t max_points, int64_t* counts, int32_t* status);
 int  pcreg_local_points_fill(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, double R,

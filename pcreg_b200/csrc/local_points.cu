@@ -10,7 +10,8 @@
 //    of a row are one contiguous run of the cell-sorted point array, exactly as the row scan of nn_grid.cu uses them --
 //    tests every point of those runs exactly, and (fill pass) sorts the hits by ORIGINAL index in shared memory so that the
 //    neighbourhood comes out in model order like the reference's masked indexing.  Cost ~ points inside the ball's bounding
-//    rows, not N_model: 10^5 keypoints on a 16 M-point model are tens of milliseconds instead of a minute.
+//    rows, not N_model: 10^5 keypoints on a 16 M-point model take 11 ms (centres visited in Morton order of their cells: the
+//    model is read from L2) instead of a minute.
 //  * models without a grid (k_local_points): order-preserving brute-force compaction -- a warp owns a chunk of 2048
 //    consecutive model points and a tile of 32 centres; the hit mask of every (32-point group, centre) is a ballot, running
 //    per-centre offsets live one per lane.  Model points are read once per 32 centres.
@@ -117,6 +118,8 @@ struct LocalGridArgs {
     const int32_t* status;              // fill pass: centres with status != 0 are skipped (may be null)
     double* out; int64_t ld_out; double* dists; int32_t* orig;
     int sort_cap;                       // fill pass: power of two >= the largest accepted count
+    const int32_t* order;               // block b works on centre order[b]: centres in Morton order of their grid cells, so that
+                                        // blocks running at the same time read the same region of the model (L2 reuse)
 };
 
 // distance from v to the slab [lo, lo + w] along one axis (0 inside), minus a rounding allowance: never too large
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(LPG_THREADS) k_local_grid(const __grid_constan
     __shared__ unsigned int s_n;
     const GridView& G = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t k = blockIdx.x;
+    const int64_t k = a.order ? (int64_t)a.order[blockIdx.x] : (int64_t)blockIdx.x;
     int64_t row0 = 0, nk = 0;
     if (FILL) {
         if (a.status && a.status[k] != 0) return;
@@ -198,23 +201,30 @@ __global__ void __launch_bounds__(LPG_THREADS) k_local_grid(const __grid_constan
             s_start[tid] = start;
             s_incl[tid] = incl + woff;
             __syncthreads();
-            // ---- the points of those runs, flattened: consecutive threads take consecutive points ----
-            for (int t = tid; t < total; t += LPG_THREADS) {
-                int lo_r = 0, hi_r = LPG_THREADS - 1;                // first run whose inclusive count exceeds t
-                while (lo_r < hi_r) {
-                    const int mid = (lo_r + hi_r) >> 1;
-                    if (s_incl[mid] > t) hi_r = mid; else lo_r = mid + 1;
+            // ---- the points of those runs, flattened: a warp takes a contiguous slice, its lanes consecutive points; a lane finds
+            //      the run of its first point by bisection and then only steps forward (32 points further is ~2 runs further) ----
+            const int per = ((total + LPG_THREADS - 1) / LPG_THREADS) * 32;
+            const int t1 = min((warp + 1) * per, total);
+            int t = warp * per + lane;
+            if (t < t1) {
+                int r = 0, hi_r = LPG_THREADS - 1;                   // first run whose inclusive count exceeds t
+                while (r < hi_r) {
+                    const int mid = (r + hi_r) >> 1;
+                    if (s_incl[mid] > t) hi_r = mid; else r = mid + 1;
                 }
-                const int excl = lo_r > 0 ? s_incl[lo_r - 1] : 0;
-                const GridPoint gp = G.pts[s_start[lo_r] + (t - excl)];
-                const double dx = __dsub_rn(gp.x, cx), dy = __dsub_rn(gp.y, cy), dz = __dsub_rn(gp.z, cz);   // pts - c (getLocalPoints.m:23)
-                double dist = 0.0;
-                if (inside(dx, dy, dz, R, R2lo, R2hi, dist)) {
-                    if (FILL) {
-                        const unsigned at = atomicAdd(&s_n, 1u);
-                        if (at < (unsigned)a.sort_cap) s_hits[at] = gp.orig;
-                    } else {
-                        ++my_hits;
+                for (; t < t1; t += 32) {
+                    while (s_incl[r] <= t) ++r;                      // t < total = s_incl[last]: stops inside the array
+                    const int excl = r > 0 ? s_incl[r - 1] : 0;
+                    const GridPoint gp = G.pts[s_start[r] + (t - excl)];
+                    const double dx = __dsub_rn(gp.x, cx), dy = __dsub_rn(gp.y, cy), dz = __dsub_rn(gp.z, cz);   // pts - c (getLocalPoints.m:23)
+                    double dist = 0.0;
+                    if (inside(dx, dy, dz, R, R2lo, R2hi, dist)) {
+                        if (FILL) {
+                            const unsigned at = atomicAdd(&s_n, 1u);
+                            if (at < (unsigned)a.sort_cap) s_hits[at] = gp.orig;
+                        } else {
+                            ++my_hits;
+                        }
                     }
                 }
             }
@@ -274,15 +284,47 @@ static bool local_grid_worthwhile(const pcreg_model* m, double R) {
     const double span = 2.0 * R * G.inv_cell + 3.0;
     return span * span <= 0.25 * (double)G.dims[0][1] * (double)G.dims[0][2] || m->n > 4000000;
 }
-static void local_grid_count(const pcreg_model* m, const double* d_c, int64_t nc, double R, int64_t* d_totals, cudaStream_t st) {
+// Centres in Morton order of their (clamped) grid cells: host-side LSD radix sort of 30-bit codes, uploaded as a permutation.
+static void local_grid_order(const pcreg_model* m, const double* centres, int64_t nc, int64_t ld, DevBuf<int32_t>& d_order, cudaStream_t st) {
+    const GridView& G = m->grid;
+    auto spread = [](uint32_t v) { v &= 0x3ffu; v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu; v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+    int shift = 0;
+    while ((std::max({G.dims[0][0], G.dims[0][1], G.dims[0][2]}) - 1) >> shift > 1023) ++shift;
+    std::vector<uint32_t> key((size_t)nc), key2((size_t)nc);
+    std::vector<int32_t> idx((size_t)nc), idx2((size_t)nc);
+    for (int64_t k = 0; k < nc; ++k) {
+        uint32_t c[3];
+        for (int ax = 0; ax < 3; ++ax) {
+            const double v = (centres[ax * ld + k] - G.origin[ax]) * G.inv_cell;
+            c[ax] = (uint32_t)std::fmin(std::fmax(v, 0.0), (double)(G.dims[0][ax] - 1)) >> shift;       // fmax(NaN, 0) = 0
+        }
+        key[(size_t)k] = spread(c[0]) | (spread(c[1]) << 1) | (spread(c[2]) << 2);
+        idx[(size_t)k] = (int32_t)k;
+    }
+    std::vector<uint32_t> cnt(1u << 15);
+    for (int pass = 0; pass < 2; ++pass) {                  // two 15-bit digits
+        const int sh = 15 * pass;
+        std::fill(cnt.begin(), cnt.end(), 0u);
+        for (int64_t k = 0; k < nc; ++k) ++cnt[(key[(size_t)k] >> sh) & 0x7fffu];
+        uint32_t run = 0;
+        for (auto& v : cnt) { const uint32_t t = v; v = run; run += t; }
+        for (int64_t k = 0; k < nc; ++k) { const uint32_t at = cnt[(key[(size_t)k] >> sh) & 0x7fffu]++; key2[at] = key[(size_t)k]; idx2[at] = idx[(size_t)k]; }
+        key.swap(key2); idx.swap(idx2);
+    }
+    d_order.alloc((size_t)nc);
+    PCREG_CUDA(cudaMemcpyAsync(d_order.p, idx.data(), (size_t)nc * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PCREG_CUDA(cudaStreamSynchronize(st));                  // idx is a local
+}
+static void local_grid_count(const pcreg_model* m, const double* d_c, int64_t nc, double R, int64_t* d_totals, const int32_t* d_order, cudaStream_t st) {
     LocalGridArgs a{};
-    a.g = m->grid; a.md = m->md.p; a.cx = d_c; a.cy = d_c + nc; a.cz = d_c + 2 * nc; a.nc = nc; a.R = R; a.totals = d_totals;
+    a.g = m->grid; a.md = m->md.p; a.cx = d_c; a.cy = d_c + nc; a.cz = d_c + 2 * nc; a.nc = nc; a.R = R; a.totals = d_totals; a.order = d_order;
     k_local_grid<false><<<(unsigned)nc, LPG_THREADS, 0, st>>>(a);
     PCREG_LAUNCHED();
 }
 static void local_grid_fill(const pcreg_model* m, const double* d_c, int64_t nc, double R, const int64_t* d_offsets, const int32_t* d_status,
-                            int64_t max_count, double* d_out, int64_t ld_out, double* d_dists, int32_t* d_orig, cudaStream_t st) {
+                            int64_t max_count, double* d_out, int64_t ld_out, double* d_dists, int32_t* d_orig, const int32_t* d_order, cudaStream_t st) {
     LocalGridArgs a{};
+    a.order = d_order;
     a.g = m->grid; a.md = m->md.p; a.cx = d_c; a.cy = d_c + nc; a.cz = d_c + 2 * nc; a.nc = nc; a.R = R;
     a.offsets = d_offsets; a.status = d_status; a.out = d_out; a.ld_out = ld_out; a.dists = d_dists; a.orig = d_orig;
     int cap = 32;
@@ -309,8 +351,10 @@ static void local_points_run(const pcreg_model* m, const double* centres, int64_
     int64_t max_count = 0;
     if (fill) for (int64_t k = 0; k < nc; ++k) if (!status_in || status_in[k] == 0) max_count = std::max(max_count, offsets[k + 1] - offsets[k]);
     if (local_grid_worthwhile(m, R) && (!fill || max_count <= LPG_MAX_HITS)) {
+        DevBuf<int32_t> d_order;
+        if (nc >= 1024) local_grid_order(m, centres, nc, ld, d_order, st);
         if (!fill) {
-            local_grid_count(m, dc.p, nc, R, totals.p, st);
+            local_grid_count(m, dc.p, nc, R, totals.p, d_order.p, st);
             PCREG_CUDA(cudaMemcpyAsync(counts_out, totals.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
             PCREG_CUDA(cudaStreamSynchronize(st));
             return;
@@ -324,7 +368,7 @@ static void local_points_run(const pcreg_model* m, const double* centres, int64_
         PCREG_CUDA(cudaMemcpyAsync(d_off.p, offsets, ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
         if (status_in) PCREG_CUDA(cudaMemcpyAsync(d_st.p, status_in, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
         local_grid_fill(m, dc.p, nc, R, d_off.p, status_in ? d_st.p : nullptr, max_count, d_out.p, (int64_t)nel, dists ? d_dist.p : nullptr,
-                        orig ? d_orig.p : nullptr, st);
+                        orig ? d_orig.p : nullptr, d_order.p, st);
         for (int k = 0; k < 3; ++k)
             PCREG_CUDA(cudaMemcpyAsync(pts_rel + (size_t)k * ld_out, d_out.p + k * nel, (size_t)ntotal * 8, cudaMemcpyDeviceToHost, st));
         if (dists) PCREG_CUDA(cudaMemcpyAsync(dists, d_dist.p, (size_t)ntotal * 8, cudaMemcpyDeviceToHost, st));
@@ -383,8 +427,10 @@ void local_points_device(const pcreg_model* m, const double* centres, int64_t nc
     a.md = m->md.p; a.n = m->n; a.cx = dc.p; a.cy = dc.p + nc; a.cz = dc.p + 2 * nc; a.nc = nc; a.R = R;
     a.chunk_cnt = cnt.p; a.nchunks = nchunks;
     dim3 grid((unsigned)nchunks, (unsigned)ntiles);
+    DevBuf<int32_t> d_order;
+    if (use_grid && nc >= 1024) local_grid_order(m, centres, nc, ld, d_order, st);
     if (use_grid) {
-        local_grid_count(m, dc.p, nc, R, totals.p, st);
+        local_grid_count(m, dc.p, nc, R, totals.p, d_order.p, st);
     } else {
         k_local_points<false><<<grid, 32, 0, st>>>(a);
         PCREG_LAUNCHED();
@@ -411,7 +457,7 @@ void local_points_device(const pcreg_model* m, const double* centres, int64_t nc
     int64_t max_count = 0;
     for (int64_t k = 0; k < nc; ++k) if (!out.status[k]) max_count = std::max(max_count, out.counts[k]);
     if (use_grid && max_count <= LPG_MAX_HITS) {
-        local_grid_fill(m, dc.p, nc, R, out.d_offsets.p, d_st.p, max_count, out.pts.p, out.nel, nullptr, nullptr, st);
+        local_grid_fill(m, dc.p, nc, R, out.d_offsets.p, d_st.p, max_count, out.pts.p, out.nel, nullptr, nullptr, d_order.p, st);
         PCREG_CUDA(cudaStreamSynchronize(st));
         return;
     }

@@ -1,13 +1,8 @@
 #!/bin/bash
-# round 2, call k10: list scan with whole trips peeled off (no predicates / far pairs in them) A/B
+# round 2, call k13: k_local_grid with per-lane forward stepping instead of a bisection per candidate: tests, timing, ncu capture
 set -x
-timeout 900 python -m pytest tests/test_gpu_voxel_map.py tests/test_gpu_icp.py -x -q 2>&1 | tail -3
-B="python bench.py --steps 3 --warmup 3 --only"
-V=pcreg_b200/variants/libpcreg_nopeel.so
-$B > gpurun_out/k10_peel.json 2>/dev/null
-PCREG_LIB=$V $B > gpurun_out/k10_nopeel.json 2>/dev/null
-$B > gpurun_out/k10_peel2.json 2>/dev/null
-PCREG_LIB=$V $B > gpurun_out/k10_nopeel2.json 2>/dev/null
-python tools/bench_brief.py gpurun_out/k10_peel.json gpurun_out/k10_nopeel.json gpurun_out/k10_peel2.json gpurun_out/k10_nopeel2.json
-python tools/c4_check.py 16384 2>&1 | tail -1
-PCREG_LIB=$V python tools/c4_check.py 16384 2>&1 | tail -1
+timeout 900 python -m pytest tests/test_gpu_local_points.py tests/test_gpu_descriptors.py tests/test_gpu_pipeline.py -x -q -s 2>&1 | tail -4
+D="python tools/local_points_run.py"
+$D > gpurun_out/plainD.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_local_grid -s 1 -c 1 -o gpurun_out/r02_full_local_grid -f $D > gpurun_out/ncuD1.log 2>&1
+cat gpurun_out/plainD.log
