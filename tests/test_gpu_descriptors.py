@@ -61,3 +61,24 @@ def test_keypoint_on_a_model_point_drops_it(pcreg):
     wf, wd = oracle.getSpacialHistogramDescriptors(model, kp, opts)
     assert np.array_equal(gd, wd)
     assert np.all(gd.sum(axis=1) == counts[status == 0] - 1)
+
+
+def test_spatial_histogram_on_a_model_with_grid_equals_grid_less(pcreg):
+    """The descriptor stage on a model WITH a uniform grid takes its neighbourhoods from the grid walk of local_points.cu
+    (device-resident variant): same surviving keypoints, same histograms as on the grid-less model and as the oracle."""
+    model, kp = _setup(300_000, 1500, 21)
+    opts = dict(min_pts=150, max_pts=6000, R=3.5, thVar=(1.1, 1.2), k=0.85, ALIGN_POINTS=True)
+    mg = pcreg.Model(model, grid=True, voxel_map=-1)
+    mb = pcreg.Model(model)
+    a = pcreg.getSpacialHistogramDescriptors(mg, kp, opts, return_status=True)
+    b = pcreg.getSpacialHistogramDescriptors(mb, kp, opts, return_status=True)
+    mg.destroy(); mb.destroy()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert a[0].shape[0] > 300
+    sel = np.arange(0, kp.shape[0], 97)
+    wf, wd = oracle.getSpacialHistogramDescriptors(model, kp[sel], opts)
+    keep = np.nonzero(a[2][sel] == 0)[0]
+    assert np.array_equal(wf, kp[sel][keep])
+    rows = np.cumsum(a[2] == 0) - 1
+    assert np.array_equal(wd, a[1][rows[sel][keep]])
