@@ -8,11 +8,13 @@
 #include <math.h>
 #include <float.h>
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
 #include "pcreg_math.cuh"
+#include "pcreg_select.cuh"
 
 namespace pcreg {
 
@@ -40,10 +42,14 @@ struct PtLoader {
     }
 };
 
-__global__ void __launch_bounds__(ALIGN_THREADS) k_align_points(const __grid_constant__ AlignArgs a) {
+// KNN = one of the kinds with a K-nearest-to-the-centroid selection (its scratch -- 17 KB of shared memory -- exists only in
+// that instantiation)
+template <bool KNN>
+__global__ void __launch_bounds__(ALIGN_THREADS, 3) k_align_points(const __grid_constant__ AlignArgs a) {
     __shared__ double red[10 * 32];
     __shared__ long long redll[32];
-    __shared__ RadixSelShared rsel;
+    __shared__ typename std::conditional<KNN, HistSelShared, int>::type hsel_store;
+    __shared__ unsigned long long red_u64[KNN ? 64 : 1];
     __shared__ double sh_coeff[9];      // coeff_unambig, row-major
     __shared__ double sh_pca[9];        // coeff before disambiguation
 
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_points(const __grid_con
     const PtLoader L{a.pts, a.is_double, a.ld, r0};
     unsigned long long* __restrict__ keys = a.keys + r0;
     const int kind = a.kind;
-    const bool knn = (kind == PCREG_ALIGN_KNN_FRAC || kind == PCREG_ALIGN_KNN_ABS || kind == PCREG_ALIGN_KNN_C);
+    constexpr bool knn = KNN;
 
     if (N <= 0) {
         if (tid == 0) {
@@ -83,17 +89,36 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_points(const __grid_con
     bool all_eq = false;
     long long K = 0;
     if (knn) {
+        unsigned long long kmin = ~0ull, kmax = 0ull;
         for (int64_t i = tid; i < N; i += ALIGN_THREADS) {
             double x, y, z;
             L.get(i, x, y, z);
-            keys[i] = dbits(norm3_exact(x - c[0], y - c[1], z - c[2]));     // AlignPoints_KNN.m:22-23
+            const unsigned long long key = dbits(norm3_exact(x - c[0], y - c[1], z - c[2]));     // AlignPoints_KNN.m:22-23
+            keys[i] = key;
+            kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
         }
         if (kind == PCREG_ALIGN_KNN_ABS) K = a.k_abs < N ? a.k_abs : N;     // AlignPoints_knn.m:12
         else                             K = (long long)floor((double)N * a.k_frac + 0.5);   // round(), AlignPoints_KNN.m:21
         if (K > N) K = N;
         if (K < 0) K = 0;
-        __syncthreads();
-        block_radix_select(keys, N, K, rsel, vK, all_eq);
+        {   // block min / max of the keys: the range of the one-pass histogram selection (pcreg_select.cuh)
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long a0 = __shfl_xor_sync(0xffffffffu, kmin, o), a1 = __shfl_xor_sync(0xffffffffu, kmax, o);
+                kmin = a0 < kmin ? a0 : kmin;
+                kmax = a1 > kmax ? a1 : kmax;
+            }
+            if (lane == 0) { red_u64[warp] = kmin; red_u64[32 + warp] = kmax; }
+            __syncthreads();
+            kmin = ~0ull; kmax = 0ull;
+            for (int w = 0; w < ALIGN_THREADS / 32; ++w) {
+                kmin = red_u64[w] < kmin ? red_u64[w] : kmin;
+                kmax = red_u64[32 + w] > kmax ? red_u64[32 + w] : kmax;
+            }
+            __syncthreads();
+        }
+        if constexpr (KNN) block_hist_select(keys, N, K, kmin, kmax, hsel_store, vK, all_eq, nullptr);
     }
 
     // ---- KNN_C: centroid of the selected relative points, then the r-ball around it ----
@@ -309,7 +334,10 @@ int pcreg_align_points(int kind, const void* pts, int is_double, int64_t ld, con
     const bool prof = ctx().profiling;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (prof) { e0 = pooled_event(0); e1 = pooled_event(1); PCREG_CUDA(cudaEventRecord(e0, st)); }
-    k_align_points<<<(unsigned)nbatch, ALIGN_THREADS, 0, st>>>(a);
+    if (a.kind == PCREG_ALIGN_KNN_FRAC || a.kind == PCREG_ALIGN_KNN_ABS || a.kind == PCREG_ALIGN_KNN_C)
+        k_align_points<true><<<(unsigned)nbatch, ALIGN_THREADS, 0, st>>>(a);
+    else
+        k_align_points<false><<<(unsigned)nbatch, ALIGN_THREADS, 0, st>>>(a);
     PCREG_LAUNCHED();
     if (prof) PCREG_CUDA(cudaEventRecord(e1, st));
     for (int k = 0; k < 3; ++k)
