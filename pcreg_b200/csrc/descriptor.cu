@@ -15,6 +15,7 @@
 #include "pcreg_internal.h"
 #include "pcreg_dev.cuh"
 #include "pcreg_math.cuh"
+#include "pcreg_select.cuh"
 
 namespace pcreg {
 
@@ -48,7 +49,8 @@ __device__ __forceinline__ int hist_bin(double x, const double* __restrict__ e, 
 __global__ void __launch_bounds__(DESC_THREADS) k_spatial_hist(const __grid_constant__ DescArgs a) {
     __shared__ double red[10 * 32];
     __shared__ long long redll[32];
-    __shared__ RadixSelShared rsel;
+    __shared__ HistSelShared hsel;
+    __shared__ unsigned long long red_u64[64];
     __shared__ double sh_pca[9], sh_coeff[9];
     __shared__ int sh_reject;
     __shared__ int hist[DESC_MAX_BINS];
@@ -78,12 +80,33 @@ __global__ void __launch_bounds__(DESC_THREADS) k_spatial_hist(const __grid_cons
         for (int64_t i = tid; i < N; i += DESC_THREADS) { s[0] += X[i]; s[1] += Y[i]; s[2] += Z[i]; }
         block_sum<3>(s, red);
         const double c0 = s[0] / (double)N, c1 = s[1] / (double)N, c2 = s[2] / (double)N;
-        for (int64_t i = tid; i < N; i += DESC_THREADS) keys[i] = dbits(norm3_exact(X[i] - c0, Y[i] - c1, Z[i] - c2));
+        unsigned long long kmin = ~0ull, kmax = 0ull;
+        for (int64_t i = tid; i < N; i += DESC_THREADS) {
+            const unsigned long long key = dbits(norm3_exact(X[i] - c0, Y[i] - c1, Z[i] - c2));
+            keys[i] = key;
+            kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+        }
         K = (long long)floor((double)N * a.k_frac + 0.5);                     // round(num_points*K), :77
         if (K > N) K = N;
         if (K < 0) K = 0;
-        __syncthreads();
-        block_radix_select(keys, N, K, rsel, vK, all_eq);
+        {   // block min / max of the keys: the range of the one-pass histogram selection (pcreg_select.cuh)
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long a0 = __shfl_xor_sync(0xffffffffu, kmin, o), a1 = __shfl_xor_sync(0xffffffffu, kmax, o);
+                kmin = a0 < kmin ? a0 : kmin;
+                kmax = a1 > kmax ? a1 : kmax;
+            }
+            if (lane == 0) { red_u64[warp] = kmin; red_u64[32 + warp] = kmax; }
+            __syncthreads();
+            kmin = ~0ull; kmax = 0ull;
+            for (int w = 0; w < DESC_THREADS / 32; ++w) {
+                kmin = red_u64[w] < kmin ? red_u64[w] : kmin;
+                kmax = red_u64[32 + w] > kmax ? red_u64[32 + w] : kmax;
+            }
+            __syncthreads();
+        }
+        block_hist_select(keys, N, K, kmin, kmax, hsel, vK, all_eq, nullptr);
     }
     auto member = [&](int64_t i) -> bool { return !a.knn || key_selected(keys[i], vK, all_eq); };
 

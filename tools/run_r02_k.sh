@@ -1,14 +1,5 @@
 #!/bin/bash
-# round 2, call k16: AlignPoints kernels: histogram selection + unrolled streaming loops vs HEAD (median of three launches)
+# round 2, call k17: descriptor kernel with the one-pass histogram selection: tests + timing
 set -x
-F="--steps 2 --warmup 3 --no-c2 --no-cpu --no-match --no-c4 --no-c5 --no-local"
-for r in 1 2; do
-python bench.py $F > gpurun_out/k16_new$r.json 2>/dev/null
-PCREG_LIB=pcreg_b200/variants/libpcreg_head.so python bench.py $F > gpurun_out/k16_head$r.json 2>/dev/null
-done
-python - <<'PY'
-import json
-for f in ('new1','head1','new2','head2'):
-    d=[json.loads(l) for l in open('gpurun_out/k16_%s.json'%f) if l.startswith('{')][0]
-    print(f, {k:(round(v['kernel_ms'],3), round(v['roofline']['frac'],3)) for k,v in d['align_batch']['variants'].items()})
-PY
+timeout 900 python -m pytest tests/test_gpu_descriptors.py tests/test_gpu_pipeline.py tests/test_gpu_golden_rows.py -x -q 2>&1 | tail -3
+python tools/desc_run.py 20000 2>&1 | tail -3
