@@ -420,10 +420,11 @@ def roofline_for(w, r):
     if w["nn"] == "grid" and p.get("fused"):
         # k_icp_fused, all passes of all hypotheses in one launch.  Per query and pass: NN = 24 B source point + 8 B voxel header
         # + 16 B per list entry scanned + 32 B per point gathered for the FP64 decision; sums = 24 B source point + 32 B model
-        # point (+ 8 B weight).  Correspondences and trim keys never leave shared memory.
+        # point (+ 8 B weight) per SELECTED correspondence.  Correspondences and trim keys never leave shared memory.
         nq = p["nn_queries"]
-        by = nq * (24.0 + 8.0 + 24.0 + 32.0 + (8.0 if w["mode"] == "weighted" else 0.0)) + 16.0 * p["list_entries_read"] + 32.0 * p["list_points_gathered"] \
-            + 36.0 * p["walked_queries"]
+        sel = 0.85 if w["mode"] == "knn" else 1.0       # trimmed mode: the sums pass reads only the selected correspondences (k_frac)
+        by = nq * (24.0 + 8.0) + nq * sel * (24.0 + 32.0 + (8.0 if w["mode"] == "weighted" else 0.0)) + 16.0 * p["list_entries_read"] \
+            + 32.0 * p["list_points_gathered"] + 36.0 * p["walked_queries"]
         ms = pt["nn_ms"]
         gbs = by / max(ms, 1e-9) / 1e6
         return dict(bound="hbm", kernel="k_icp_fused", achieved=gbs, peak=peak, unit="GB/s", frac=gbs / peak, traffic=ncu_traffic("k_icp_fused"),
