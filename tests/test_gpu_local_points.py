@@ -145,4 +145,11 @@ def test_local_points_16m_model_1e5_keypoints(pcreg):
             n_ok += 1
             assert np.array_equal(got[k][0], wp) and np.array_equal(got[k][1], wd)
     assert n_ok >= 3
+    # neighbourhoods larger than the shared-memory sort of the grid path (32 768 hits): counted on the grid, filled by the
+    # order-preserving brute-force compaction -- same answer
+    big = kp[:3]
+    got = pcreg.getLocalPoints_batch(m, big, 4.2, 0, np.inf, return_idx=True)
+    assert max(g[0].shape[0] for g in got) > 32768
+    wp, wd = oracle.getLocalPoints(model, 4.2, big[1], 0, np.inf)
+    assert np.array_equal(got[1][0], wp) and np.array_equal(got[1][1], wd) and np.all(np.diff(got[1][2]) > 0)
     m.destroy()
