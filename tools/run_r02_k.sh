@@ -1,4 +1,4 @@
 #!/bin/bash
-# round 2, call k21: getLocalPoints test incl. the >32768-hit fallback of the grid path
+# round 2, call k22: model creation breakdown on C5 / C4 / C3 (per-level voxel build log)
 set -x
-timeout 900 python -m pytest tests/test_gpu_local_points.py -x -q -s 2>&1 | tail -4
+for c in c5 c4 c3; do python tools/vox_build_times.py $c 2>&1 | grep -E "pcreg vox|create" | cut -c1-220; done
